@@ -1,0 +1,162 @@
+/*
+ * mcvd_b200 -- C ABI of the B200-native MCVD DDPM-sampling hot path.
+ *
+ * Plain C: device pointers and sizes only, no torch types.  Every pointer is a BORROWED device
+ * pointer (owned by the caller, normally a torch tensor); outputs and workspaces are caller
+ * allocated; every launch goes to the cudaStream_t passed in; no call synchronises.
+ * Return value: 0 on success, negative on error (text via mcvd_last_error()).
+ *
+ * What this replaces in the reference (voletiv/mcvd-pytorch @ 451da2e, paths relative to its root):
+ *   - the only native surface the reference has is the pybind11 op
+ *       upfirdn2d(Tensor input, Tensor kernel, int up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+ *     (models/better/op/upfirdn2d.cpp:11-22, upfirdn2d_kernel.cu:209-369) -> MCVD_OP_APPLY with
+ *     MCVD_F_UP / MCVD_F_DOWN (the FIR is fused with the norm/activation that precedes it);
+ *   - everything else on the path is ATen/cuDNN/cuBLAS reached from Python
+ *     (models/better/layerspp.py, layers.py, ncsnpp_more.py, models/__init__.py); the op kinds below
+ *     are the fused B200 equivalents, each citing the reference lines it stands for.
+ *
+ * The host side (mcvd_b200/program.py) lowers a network + sampler step into an array of McvdOp and
+ * calls mcvd_run_program() once per network evaluation (or once per CUDA-graph capture).
+ */
+#ifndef MCVD_B200_H
+#define MCVD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCVD_ABI_VERSION 1
+
+/* ---- op kinds ------------------------------------------------------------------------------- */
+enum {
+  /* [B,C0,H,W] (+ [B,C1,H,W]) fp32 NCHW -> [B,H,W,C0+C1] NHWC.  torch.cat([x, cond], 1) +
+   * x.contiguous() of ncsnpp_more.py:256-257,293. */
+  MCVD_OP_NCHW_TO_NHWC = 1,
+  /* [B,H,W,C0] NHWC -> [B,C0,H,W] NCHW (network output back to the reference layout). */
+  MCVD_OP_NHWC_TO_NCHW = 2,
+  /* sinusoidal timestep embedding, layers.py:504-518.  src0 = t fp32 [B]; dst [B, Cout]. */
+  MCVD_OP_TIMESTEP_EMBED = 3,
+  /* dst[b,j] = bias[j] + sum_k act(src0[b,k]) * w[j,k]; w is nn.Linear layout [Cout, C0].
+   * MCVD_F_ACT_IN applies SiLU to the input (temb MLP ncsnpp_more.py:278-280; every FiLM
+   * projection Dense_0(act(temb)) layerspp.py:521).  B rows. */
+  MCVD_OP_LINEAR = 4,
+  /* GroupNorm statistics, pass 1: per (b, pixel-chunk, channel) sum / sum-of-squares in fp64.
+   * src0 [B,H,W,C0] (+ src1 [B,H,W,C1], virtual channel concat); dst = double2 [B, i0, C0+C1],
+   * i0 = number of pixel chunks. */
+  MCVD_OP_GN_PARTIAL = 5,
+  /* GroupNorm statistics, pass 2 + FiLM/affine folding: reduces the partials over chunks and over
+   * the i1 = C/groups channels of a group (groups are contiguous channel ranges,
+   * layerspp.py:474-477), and writes one float4 per (b, channel): (mean, rstd, G, S) so that the
+   * consumer computes  y = ((x - mean) * rstd [*(1+gamma)+beta]) * G + S.
+   *   aux0 != NULL, MCVD_F_FILM : G = 1 + aux0[b*i2 + i3 + c], S = aux0[b*i2 + i3 + C + c]
+   *                               (scale/shift = chunk(Dense_0(act(temb)), 2), layerspp.py:521-523,536)
+   *   aux0 != NULL, !FILM       : G = aux0[c] (GroupNorm weight), S = aux1[c] (bias)
+   *   aux0 == NULL              : G = 1, S = 0
+   * src0 = partials, i0 = chunks, C0 = total channels, f0 = eps, f1 = 1/(pixels * i1). */
+  MCVD_OP_GN_FINALIZE = 6,
+  /* normalise + FiLM (+ SPADE gamma/beta) + SiLU + optional 4x4 FIR up/down-sampling, fp32 NHWC in
+   * and out.  get_act_norm.forward layerspp.py:518-549, MySPADE.forward :152-173 (norm part),
+   * upsample_2d / downsample_2d up_or_down_sampling.py:196-258 == upfirdn2d.  H,W are OUTPUT
+   * dims; src0/src1 are the (virtually concatenated) inputs at input resolution; aux0 = float4
+   * table from GN_FINALIZE (NULL = raw pass-through, used for the skip branch FIR(x));
+   * aux1/aux2 = SPADE gamma/beta [B,Hin,Win,C] or NULL. */
+  MCVD_OP_APPLY = 7,
+  /* direct convolution as implicit GEMM on CUDA cores (fp32 FFMA), NHWC.  nn.Conv2d 3x3 pad 1 /
+   * 1x1 (layers.py:89-113) and NIN (layers.py:541-544).  i0 = ksize (1|3); src0/src1 virtual
+   * concat; w = packed [taps][C0+C1][i1] fp32 (i1 = Cout rounded up to 4); bias [Cout];
+   * aux0 = residual [B,H,W,Cout] or NULL; dst = f0 * (conv + bias + residual);
+   * MCVD_F_ACT_OUT applies SiLU to the result (SPADE mlp_shared, layerspp.py:148). */
+  MCVD_OP_CONV_SIMT = 8,
+  /* softmax(q.k^T * f0) v over all H*W keys, per (b, head); AttnBlockpp.forward layerspp.py:239-245.
+   * src0 = qkv [B, T, 3*C0] (q | k | v along channels), i0 = heads, i1 = head dim, T = H*W;
+   * dst [B, T, C0]. */
+  MCVD_OP_ATTENTION = 9,
+  /* nearest-neighbour resize of an NHWC map (F.interpolate(segmap, 'nearest'), layerspp.py:165).
+   * src0 [B, i0, i1, C0] -> dst [B, H, W, C0]. */
+  MCVD_OP_RESIZE_NEAREST = 10,
+  /* reverse-diffusion update on the NCHW state, in place (models/__init__.py:287-290,324-333 for
+   * DDPM; :163-166 DDIM; denoise :331-333):
+   *   x0 = f0 * (x - f1 * eps);  if MCVD_F_CLIP: x0 = clamp(x0,-1,1);
+   *   x  = f2 * x0 + f3 * x + f4 * eps + f5 * z
+   * dst = x [B,C0,H,W] NCHW (in place); src0 = eps [B,H,W,C0] NHWC; src1 = z NCHW or NULL
+   * (MCVD_F_PHILOX: z from Philox4x32-10 keyed by (seed=i0|i1<<32, clip id = i2 + b, step = i3)). */
+  MCVD_OP_DIFFUSION_UPDATE = 11,
+  /* 3x3 / 1x1 convolution on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp16 hi/lo split of
+   * both operands, fp32 accumulation in TMEM), with the GroupNorm/FiLM/SiLU transform of the input
+   * fused into the shared-memory staging.  Same semantics as MCVD_OP_CONV_SIMT; see
+   * mcvd_b200/csrc/conv_umma.cu. */
+  MCVD_OP_CONV_UMMA = 12,
+  /* final 3x3 conv with tiny Cout (<= 16) and fused input norm: conv3x3(SiLU(GN(x))) of
+   * ncsnpp_more.py:375-379; aux0 = float4 norm table or NULL. */
+  MCVD_OP_CONV_SMALLN = 13,
+  /* dst[i] = src0[i] (i0 floats) -- device-to-device copy inside a program. */
+  MCVD_OP_COPY = 14,
+  MCVD_OP__COUNT
+};
+
+/* ---- flags ---------------------------------------------------------------------------------- */
+#define MCVD_F_ACT_IN   (1 << 0)   /* SiLU on the input (LINEAR)                                   */
+#define MCVD_F_ACT_OUT  (1 << 1)   /* SiLU on the output (APPLY: after the norm; CONV: on result)  */
+#define MCVD_F_UP       (1 << 2)   /* APPLY: FIR upsample x2   (input is H/2 x W/2)               */
+#define MCVD_F_DOWN     (1 << 3)   /* APPLY: FIR downsample x2 (input is 2H x 2W)                 */
+#define MCVD_F_FILM     (1 << 4)   /* GN_FINALIZE: aux0 is the FiLM table                          */
+#define MCVD_F_CLIP     (1 << 5)   /* DIFFUSION_UPDATE: clamp x0 to [-1, 1]                        */
+#define MCVD_F_PHILOX   (1 << 6)   /* DIFFUSION_UPDATE: draw z in-kernel                           */
+
+typedef struct McvdOp {
+  int32_t kind;
+  int32_t flags;
+  int32_t B, H, W;          /* batch and OUTPUT spatial size                                   */
+  int32_t C0, C1;           /* channels of src0 / src1 (C1 = 0: no second source)               */
+  int32_t Cout;
+  int32_t i0, i1, i2, i3;   /* per-kind integers, see the kind's comment                         */
+  float f0, f1, f2, f3, f4, f5, f6, f7;
+  const void* src0;
+  const void* src1;
+  const void* w;
+  const void* bias;
+  const void* aux0;
+  const void* aux1;
+  const void* aux2;
+  void* dst;
+  void* dst2;
+} McvdOp;
+
+/* Library / ABI identification. */
+int mcvd_abi_version(void);
+/* sizeof(McvdOp) as compiled -- the Python ctypes mirror asserts equality at load time. */
+int mcvd_sizeof_op(void);
+/* Text of the last error on the calling thread ("" if none). */
+const char* mcvd_last_error(void);
+/* Compute capability of the current device as major*10+minor (e.g. 100), or <0. */
+int mcvd_device_arch(void);
+
+/* Launch ops[0..n) in order on `stream` (a cudaStream_t).  No synchronisation, re-entrant, uses the
+ * device of the calling thread's current CUDA context (torch.cuda.device).  Capturable in a CUDA
+ * graph. */
+int mcvd_run_program(const McvdOp* ops, int n, void* stream);
+
+/* Validate a program on the host without launching (shapes, alignment, NULLs).  Works without a
+ * GPU. */
+int mcvd_validate_program(const McvdOp* ops, int n);
+
+/* Number of kernel launches mcvd_run_program would issue for this program (bench.py's
+ * gpu_launches). */
+int mcvd_count_launches(const McvdOp* ops, int n);
+
+/* Weight packing for MCVD_OP_CONV_UMMA (device -> device, on `stream`):
+ * w_taps = fp32 [taps][Cin][Cout] (the CONV_SIMT layout without Cout padding); out = the fp16 hi/lo
+ * shared-memory images consumed by the tensor-core kernel; returns bytes required when out == NULL.
+ * scale_log2 receives the power-of-two pre-scale applied to the weights (undone in the epilogue). */
+long long mcvd_umma_pack_weights(const float* w_taps, int taps, int Cin, int Cout, int n_tile, int k_block,
+                                 void* out, int scale_log2, void* stream);
+/* Channels per K-block (32, 16, or 0 = unsupported) the tensor-core conv uses for sources with C0 / C1
+ * channels; the packed weights must be produced with the same value. */
+int mcvd_umma_kblock(int C0, int C1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCVD_B200_H */

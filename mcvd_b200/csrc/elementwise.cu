@@ -1,0 +1,466 @@
+// Memory-bound kernels of the MCVD sampling path: layout changes, timestep embedding, FiLM linears,
+// GroupNorm statistics, the fused normalise/FiLM/SPADE/SiLU/FIR "apply" pass, nearest resize and
+// the reverse-diffusion update.  All tensors fp32; activations NHWC.
+#include "mcvd_common.cuh"
+
+namespace mcvd {
+
+// ------------------------------------------------------------------------------------------------
+// NCHW (+NCHW) -> NHWC  /  NHWC -> NCHW
+// ------------------------------------------------------------------------------------------------
+__global__ void k_nchw_to_nhwc(const float* __restrict__ s0, const float* __restrict__ s1, float* __restrict__ dst,
+                               int B, int HW, int C0, int C1) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  int b = (int)(i / HW), p = (int)(i % HW);
+  int C = C0 + C1;
+  float* d = dst + i * C;
+  for (int c = 0; c < C0; ++c) d[c] = s0[((long long)b * C0 + c) * HW + p];
+  for (int c = 0; c < C1; ++c) d[C0 + c] = s1[((long long)b * C1 + c) * HW + p];
+}
+
+int launch_nchw_to_nhwc(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst && (op.C1 == 0 || op.src1), "NCHW_TO_NHWC: null pointer");
+  long long n = (long long)op.B * op.H * op.W;
+  k_nchw_to_nhwc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)op.src0, (const float*)op.src1,
+                                                             (float*)op.dst, op.B, op.H * op.W, op.C0, op.C1);
+  MCVD_CUDA_LAUNCH_CHECK("nchw_to_nhwc");
+  return 0;
+}
+
+__global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int B, int HW, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * HW) return;
+  int b = (int)(i / HW), p = (int)(i % HW);
+  const float* sp = src + i * C;
+  for (int c = 0; c < C; ++c) dst[((long long)b * C + c) * HW + p] = sp[c];
+}
+
+int launch_nhwc_to_nchw(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "NHWC_TO_NCHW: null pointer");
+  long long n = (long long)op.B * op.H * op.W;
+  k_nhwc_to_nchw<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)op.src0, (float*)op.dst, op.B,
+                                                             op.H * op.W, op.C0);
+  MCVD_CUDA_LAUNCH_CHECK("nhwc_to_nchw");
+  return 0;
+}
+
+__global__ void k_copy(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) dst[i] = src[i];
+}
+
+int launch_copy(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "COPY: null pointer");
+  long long n = (long long)op.i0 + ((long long)op.i1 << 31);
+  unsigned g = (unsigned)((n + 255) / 256);
+  if (g > 148 * 16) g = 148 * 16;
+  if (g == 0) g = 1;
+  k_copy<<<g, 256, 0, s>>>((const float*)op.src0, (float*)op.dst, n);
+  MCVD_CUDA_LAUNCH_CHECK("copy");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding: dst[b, k] = sin(t_b * f_k), dst[b, half + k] = cos(t_b * f_k)
+// f_k comes from the host (computed exactly as the reference does, layers.py:508-511) so the
+// argument t*f is bit-identical to the reference's; only sinf/cosf differ (<= 2 ulp).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_timestep_embed(const float* __restrict__ t, const float* __restrict__ freqs,
+                                 float* __restrict__ dst, int B, int dim) {
+  int half = dim / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  int b = i / dim, k = i % dim;
+  float v = 0.f;
+  if (k < half) v = sinf(t[b] * freqs[k]);
+  else if (k < 2 * half) v = cosf(t[b] * freqs[k - half]);
+  dst[i] = v;
+}
+
+int launch_timestep_embed(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.w && op.dst, "TIMESTEP_EMBED: null pointer");
+  int n = op.B * op.Cout;
+  k_timestep_embed<<<cdiv(n, 256), 256, 0, s>>>((const float*)op.src0, (const float*)op.w, (float*)op.dst, op.B,
+                                                op.Cout);
+  MCVD_CUDA_LAUNCH_CHECK("timestep_embed");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// linear: dst[b, j] = act_out(bias[j] + sum_k act_in(src[b, k]) * w[j, k]);  one warp per output j
+// ------------------------------------------------------------------------------------------------
+constexpr int LIN_BT = 16;
+
+__global__ void __launch_bounds__(128) k_linear(const float* __restrict__ src, const float* __restrict__ w,
+                                                const float* __restrict__ bias, float* __restrict__ dst, int B,
+                                                int K, int N, int flags) {
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int j = blockIdx.x * 4 + warp;
+  if (j >= N) return;
+  const float* wr = w + (long long)j * K;
+  for (int b0 = 0; b0 < B; b0 += LIN_BT) {
+    float acc[LIN_BT];
+#pragma unroll
+    for (int i = 0; i < LIN_BT; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      float wv = wr[k];
+#pragma unroll
+      for (int i = 0; i < LIN_BT; ++i) {
+        if (b0 + i < B) {
+          float xv = src[(long long)(b0 + i) * K + k];
+          if (flags & MCVD_F_ACT_IN) xv = silu_f(xv);
+          acc[i] = fmaf(wv, xv, acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LIN_BT; ++i) {
+      float v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && b0 + i < B) {
+        v += bias ? bias[j] : 0.f;
+        if (flags & MCVD_F_ACT_OUT) v = silu_f(v);
+        dst[(long long)(b0 + i) * N + j] = v;
+      }
+    }
+  }
+}
+
+int launch_linear(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.w && op.dst, "LINEAR: null pointer");
+  k_linear<<<cdiv(op.Cout, 4), 128, 0, s>>>((const float*)op.src0, (const float*)op.w, (const float*)op.bias,
+                                            (float*)op.dst, op.B, op.C0, op.Cout, op.flags);
+  MCVD_CUDA_LAUNCH_CHECK("linear");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm statistics.  Pass 1: grid (chunks, B), 4 warps; a warp owns 32-channel blocks
+// round-robin and walks the chunk's pixels (128 B coalesced per pixel).  Deterministic.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_gn_partial(const float* __restrict__ s0, const float* __restrict__ s1,
+                                                    double2* __restrict__ part, int HW, int C0, int C1,
+                                                    int nchunk, int ppc) {
+  int b = blockIdx.y, chunk = blockIdx.x;
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int C = C0 + C1;
+  int p0 = chunk * ppc, p1 = min(p0 + ppc, HW);
+  for (int cb = warp * 32; cb < C; cb += 128) {
+    int c = cb + lane;
+    if (c >= C) continue;
+    const float* src;
+    int cs, cc;
+    if (c < C0) { src = s0; cs = C0; cc = c; } else { src = s1; cs = C1; cc = c - C0; }
+    const float* ptr = src + ((long long)b * HW + p0) * cs + cc;
+    double ds = 0.0, dq = 0.0;
+    int p = p0;
+    while (p < p1) {
+      int pe = min(p + 32, p1);
+      float fs = 0.f, fq = 0.f;
+      for (; p < pe; ++p) {
+        float v = *ptr;
+        ptr += cs;
+        fs += v;
+        fq = fmaf(v, v, fq);
+      }
+      ds += (double)fs;
+      dq += (double)fq;
+    }
+    part[((long long)b * nchunk + chunk) * C + c] = make_double2(ds, dq);
+  }
+}
+
+int launch_gn_partial(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst && (op.C1 == 0 || op.src1), "GN_PARTIAL: null pointer");
+  int HW = op.H * op.W;
+  int nchunk = op.i0;
+  MCVD_CHECK(nchunk >= 1, "GN_PARTIAL: chunks < 1");
+  int ppc = cdiv(HW, nchunk);
+  dim3 grid(nchunk, op.B);
+  k_gn_partial<<<grid, 128, 0, s>>>((const float*)op.src0, (const float*)op.src1, (double2*)op.dst, HW, op.C0,
+                                    op.C1, nchunk, ppc);
+  MCVD_CUDA_LAUNCH_CHECK("gn_partial");
+  return 0;
+}
+
+// Pass 2: grid (groups, B); reduce partials, emit (mean, rstd, G, S) per channel.
+__global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__ part, float4* __restrict__ tab,
+                                                     const float* __restrict__ aux0, const float* __restrict__ aux1,
+                                                     int C, int cg, int nchunk, int HW, float eps, int film,
+                                                     int film_stride, int film_off) {
+  int g = blockIdx.x, b = blockIdx.y;
+  int n = nchunk * cg;
+  double ds = 0.0, dq = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int chunk = i / cg, ci = i % cg;
+    double2 v = part[((long long)b * nchunk + chunk) * C + g * cg + ci];
+    ds += v.x;
+    dq += v.y;
+  }
+  __shared__ double sh[2][4];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dq += __shfl_xor_sync(0xffffffffu, dq, o);
+  }
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][warp] = ds; sh[1][warp] = dq; }
+  __syncthreads();
+  ds = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
+  dq = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+  double cnt = (double)HW * (double)cg;
+  double mean = ds / cnt;
+  double var = dq / cnt - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  float fmean = (float)mean;
+  for (int ci = threadIdx.x; ci < cg; ci += blockDim.x) {
+    int c = g * cg + ci;
+    float G = 1.f, S = 0.f;
+    if (aux0) {
+      if (film) {
+        G = 1.f + aux0[(long long)b * film_stride + film_off + c];
+        S = aux0[(long long)b * film_stride + film_off + C + c];
+      } else {
+        G = aux0[c];
+        S = aux1[c];
+      }
+    }
+    tab[(long long)b * C + c] = make_float4(fmean, rstd, G, S);
+  }
+}
+
+int launch_gn_finalize(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "GN_FINALIZE: null pointer");
+  int C = op.C0, cg = op.i1;
+  MCVD_CHECK(cg > 0 && C % cg == 0, "GN_FINALIZE: channels %d not divisible by group size %d", C, cg);
+  int film = (op.flags & MCVD_F_FILM) ? 1 : 0;
+  MCVD_CHECK(!op.aux0 || film || op.aux1, "GN_FINALIZE: affine needs weight and bias");
+  dim3 grid(C / cg, op.B);
+  k_gn_finalize<<<grid, 128, 0, s>>>((const double2*)op.src0, (float4*)op.dst, (const float*)op.aux0,
+                                     (const float*)op.aux1, C, cg, op.i0, op.H * op.W, op.f0, film, op.i2, op.i3);
+  MCVD_CUDA_LAUNCH_CHECK("gn_finalize");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// apply: y = act( ((x - mean) * rstd [*(1+gamma)+beta]) * G + S ), optionally through the 4x4 FIR
+// up/down-sampler.  One thread = 4 consecutive channels of one OUTPUT pixel.
+// FIR taps: outer([1,3,3,1])/64 (down) or /16 (up, gain 4) -- up_or_down_sampling.py:182-258.
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const float* s0;
+  const float* s1;
+  const float4* tab;
+  const float* gam;
+  const float* bet;
+  float* dst;
+  int B, H, W, Hin, Win, C0, C1, flags;
+};
+
+__device__ __forceinline__ float4 apply_fetch(const ApplyArgs& a, int b, int yi, int xi, int c, const float4 t[4]) {
+  // value of the transformed input at input pixel (yi, xi), channels c..c+3 (zero outside)
+  if (yi < 0 || yi >= a.Hin || xi < 0 || xi >= a.Win) return make_float4(0.f, 0.f, 0.f, 0.f);
+  long long pix = ((long long)b * a.Hin + yi) * a.Win + xi;
+  float4 v;
+  if (c < a.C0) v = *reinterpret_cast<const float4*>(a.s0 + pix * a.C0 + c);
+  else v = *reinterpret_cast<const float4*>(a.s1 + pix * a.C1 + (c - a.C0));
+  if (a.tab) {
+    float r[4] = {v.x, v.y, v.z, v.w};
+    float gm[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
+    if (a.gam) {
+      int C = a.C0 + a.C1;
+      float4 g4 = *reinterpret_cast<const float4*>(a.gam + pix * C + c);
+      float4 b4 = *reinterpret_cast<const float4*>(a.bet + pix * C + c);
+      gm[0] = g4.x; gm[1] = g4.y; gm[2] = g4.z; gm[3] = g4.w;
+      bt[0] = b4.x; bt[1] = b4.y; bt[2] = b4.z; bt[3] = b4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float n = (r[i] - t[i].x) * t[i].y;
+      if (a.gam) n = n * (1.f + gm[i]) + bt[i];
+      n = n * t[i].z + t[i].w;
+      if (a.flags & MCVD_F_ACT_OUT) n = silu_f(n);
+      r[i] = n;
+    }
+    v = make_float4(r[0], r[1], r[2], r[3]);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
+  acc.x = fmaf(w, v.x, acc.x);
+  acc.y = fmaf(w, v.y, acc.y);
+  acc.z = fmaf(w, v.z, acc.z);
+  acc.w = fmaf(w, v.w, acc.w);
+}
+
+__global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
+  int C = a.C0 + a.C1;
+  int C4 = C >> 2;
+  long long total = (long long)a.B * a.H * a.W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C4) * 4;
+    long long pix = i / C4;
+    int x = (int)(pix % a.W);
+    int y = (int)((pix / a.W) % a.H);
+    int b = (int)(pix / ((long long)a.W * a.H));
+    float4 t[4];
+    if (a.tab) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[k] = a.tab[(long long)b * C + c + k];
+    }
+    float4 out;
+    if (a.flags & MCVD_F_DOWN) {
+      // out[y,x] = sum_{i,j} k[i]k[j]/64 * in[2y+i-1, 2x+j-1]
+      const float kw[4] = {1.f, 3.f, 3.f, 1.f};
+      out = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float4 v = apply_fetch(a, b, 2 * y + ii - 1, 2 * x + jj - 1, c, t);
+          fma4(out, kw[ii] * kw[jj] * (1.f / 64.f), v);
+        }
+    } else if (a.flags & MCVD_F_UP) {
+      // even y=2a: (in[a-1] + 3 in[a]) / 4 ; odd y=2a+1: (3 in[a] + in[a+1]) / 4   (per axis)
+      int ya = y >> 1, xa = x >> 1;
+      int y0, y1, x0, x1;
+      float wy0, wy1, wx0, wx1;
+      if (y & 1) { y0 = ya; y1 = ya + 1; wy0 = 3.f; wy1 = 1.f; } else { y0 = ya - 1; y1 = ya; wy0 = 1.f; wy1 = 3.f; }
+      if (x & 1) { x0 = xa; x1 = xa + 1; wx0 = 3.f; wx1 = 1.f; } else { x0 = xa - 1; x1 = xa; wx0 = 1.f; wx1 = 3.f; }
+      out = make_float4(0.f, 0.f, 0.f, 0.f);
+      fma4(out, wy0 * wx0 * (1.f / 16.f), apply_fetch(a, b, y0, x0, c, t));
+      fma4(out, wy0 * wx1 * (1.f / 16.f), apply_fetch(a, b, y0, x1, c, t));
+      fma4(out, wy1 * wx0 * (1.f / 16.f), apply_fetch(a, b, y1, x0, c, t));
+      fma4(out, wy1 * wx1 * (1.f / 16.f), apply_fetch(a, b, y1, x1, c, t));
+    } else {
+      out = apply_fetch(a, b, y, x, c, t);
+    }
+    *reinterpret_cast<float4*>(a.dst + pix * C + c) = out;
+  }
+}
+
+int launch_apply(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst && (op.C1 == 0 || op.src1), "APPLY: null pointer");
+  MCVD_CHECK(op.C0 % 4 == 0 && op.C1 % 4 == 0, "APPLY: channels must be multiples of 4 (%d, %d)", op.C0, op.C1);
+  MCVD_CHECK(!(op.aux1) || (op.aux2 && op.aux0), "APPLY: SPADE needs gamma, beta and the norm table");
+  ApplyArgs a;
+  a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.tab = (const float4*)op.aux0;
+  a.gam = (const float*)op.aux1; a.bet = (const float*)op.aux2; a.dst = (float*)op.dst;
+  a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.flags = op.flags;
+  a.Hin = op.H; a.Win = op.W;
+  if (op.flags & MCVD_F_DOWN) { a.Hin = op.H * 2; a.Win = op.W * 2; }
+  if (op.flags & MCVD_F_UP) {
+    MCVD_CHECK(op.H % 2 == 0 && op.W % 2 == 0, "APPLY: upsample output must be even");
+    a.Hin = op.H / 2; a.Win = op.W / 2;
+  }
+  long long total = (long long)op.B * op.H * op.W * ((op.C0 + op.C1) / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  if (blocks < 1) blocks = 1;
+  k_apply<<<(unsigned)blocks, 256, 0, s>>>(a);
+  MCVD_CUDA_LAUNCH_CHECK("apply");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest resize (F.interpolate(mode='nearest'): src index = floor(dst index * in / out))
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resize_nearest(const float* __restrict__ src, float* __restrict__ dst, int B, int Hin, int Win,
+                                 int H, int W, int C) {
+  long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    long long pix = i / C;
+    int x = (int)(pix % W), y = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    // PyTorch 'nearest': src = min(floor(dst * scale), in - 1), scale = in / out (float)
+    float sy = (float)Hin / (float)H, sx = (float)Win / (float)W;
+    int yi = min((int)floorf(y * sy), Hin - 1), xi = min((int)floorf(x * sx), Win - 1);
+    dst[i] = src[(((long long)b * Hin + yi) * Win + xi) * C + c];
+  }
+}
+
+int launch_resize_nearest(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "RESIZE_NEAREST: null pointer");
+  long long total = (long long)op.B * op.H * op.W * op.C0;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  k_resize_nearest<<<(unsigned)blocks, 256, 0, s>>>((const float*)op.src0, (float*)op.dst, op.B, op.i0, op.i1, op.H,
+                                                    op.W, op.C0);
+  MCVD_CUDA_LAUNCH_CHECK("resize_nearest");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse-diffusion update (DDPM / DDIM / denoise), optional in-kernel Philox4x32-10 normal noise.
+// The Philox stream is keyed by (seed, global clip id, step, element) so a clip draws the same noise
+// whichever GPU owns it (multi-GPU equivalence).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float philox_normal(uint32_t seed_lo, uint32_t seed_hi, uint32_t clip, uint32_t step,
+                                               uint32_t elem) {
+  uint32_t r[4];
+  philox4x32_10(elem, clip, step, 0x4d435644u /* 'MCVD' */, seed_lo, seed_hi, r);
+  // Box-Muller on two 32-bit uniforms in (0,1]
+  float u1 = ((float)r[0] + 1.0f) * 2.3283064365386963e-10f;
+  float u2 = ((float)r[1] + 0.5f) * 2.3283064365386963e-10f;
+  u1 = fminf(fmaxf(u1, 1e-12f), 1.0f);
+  float rad = sqrtf(-2.0f * logf(u1));
+  return rad * cospif(2.0f * u2);
+}
+
+__global__ void k_diffusion_update(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
+                                   int B, int C, int HW, float k0, float k1, float ca, float cb, float cc,
+                                   float sigma, int flags, uint32_t seed_lo, uint32_t seed_hi, int clip0, int step) {
+  long long total = (long long)B * C * HW;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int p = (int)(i % HW);
+  int c = (int)((i / HW) % C);
+  int b = (int)(i / ((long long)HW * C));
+  float xv = x[i];
+  float ev = eps[((long long)b * HW + p) * C + c];
+  float x0 = k0 * (xv - k1 * ev);
+  if (flags & MCVD_F_CLIP) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+  float r = ca * x0 + cb * xv;
+  if (cc != 0.f) r += cc * ev;
+  if (sigma != 0.f) {
+    float zv;
+    if (flags & MCVD_F_PHILOX) zv = philox_normal(seed_lo, seed_hi, (uint32_t)(clip0 + b), (uint32_t)step, (uint32_t)(c * HW + p));
+    else zv = z[i];
+    r += sigma * zv;
+  }
+  x[i] = r;
+}
+
+int launch_diffusion_update(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "DIFFUSION_UPDATE: null pointer");
+  MCVD_CHECK(op.f5 == 0.f || (op.flags & MCVD_F_PHILOX) || op.src1, "DIFFUSION_UPDATE: sigma != 0 needs noise");
+  long long total = (long long)op.B * op.C0 * op.H * op.W;
+  k_diffusion_update<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+      (float*)op.dst, (const float*)op.src0, (const float*)op.src1, op.B, op.C0, op.H * op.W, op.f0, op.f1, op.f2,
+      op.f3, op.f4, op.f5, op.flags, (uint32_t)op.i0, (uint32_t)op.i1, op.i2, op.i3);
+  MCVD_CUDA_LAUNCH_CHECK("diffusion_update");
+  return 0;
+}
+
+}  // namespace mcvd

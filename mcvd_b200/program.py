@@ -1,0 +1,497 @@
+"""Lowering of the score network (and one reverse-diffusion step) to a C-ABI op program.
+
+``Engine`` owns, per module instance: the packed weights (repacked lazily when a parameter's version
+counter changes -- ``load_state_dict`` / ``EMAHelper.ema`` modify parameters after construction), and
+one ``Program`` per batch size: statically allocated NHWC activation buffers plus three ctypes op
+arrays
+
+  * ``cond_ops``  -- everything that depends on ``cond`` only (SPADE: the 3 conv3x3 per norm that
+                     produce gamma/beta, reference layerspp.py:165-168; they are independent of t and
+                     x, so a sampler call runs them ONCE instead of L+1 times),
+  * ``step_ops``  -- one evaluation eps = net(x, t, cond),
+  * ``update_op`` -- the DDPM/DDIM update of the NCHW state, in place.
+
+The walk below follows ``NCSNpp.forward`` / ``SPADE_NCSNpp.forward`` (reference
+models/better/ncsnpp_more.py:251-392, 590-718) module by module.
+"""
+from __future__ import annotations
+
+import contextlib
+import math
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import arch, lib
+from .lib import McvdOp
+
+INV_SQRT2 = float(1.0 / math.sqrt(2.0))
+GN_PPC = 64          # pixels per chunk in the GroupNorm partial pass
+
+
+class Src:
+    """A (possibly virtually concatenated) NHWC activation: channels of t0 followed by channels of t1."""
+
+    def __init__(self, t0, c0, t1=None, c1=0):
+        self.t0, self.c0, self.t1, self.c1 = t0, c0, t1, c1
+
+    @property
+    def C(self):
+        return self.c0 + self.c1
+
+
+def _ptr(t) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _pick_nt(cout: int) -> int:
+    best = 0
+    for d in range(16, 257, 16):
+        if cout % d == 0:
+            best = d
+    return best
+
+
+class Program:
+    def __init__(self):
+        self.keep: List[torch.Tensor] = []
+        self.cond_ops: List[McvdOp] = []
+        self.step_ops: List[McvdOp] = []
+        self.cond_arr = None
+        self.step_arr = None
+        self.update_arr = None
+        self.n_umma = 0
+        self.n_simt = 0
+
+
+class Engine:
+    def __init__(self, module, _test_backend=None):
+        """``_test_backend`` is a seam for the CPU test-suite only (tests/op_interpreter.py executes the
+        lowered program so the host logic can be checked without a GPU).  Product code never passes it:
+        without it the engine requires a CUDA device and the sm_100a library, and fails loudly."""
+        self.module = module
+        self.spec: arch.NetSpec = module.spec
+        self.device = next(module.parameters()).device
+        self.backend = _test_backend
+        self.lib = lib.load()
+        if self.backend is None:
+            if self.device.type != "cuda":
+                raise RuntimeError("mcvd_b200: the module must live on a CUDA device (no CPU fallback)")
+            with torch.cuda.device(self.device):
+                cc = self.lib.mcvd_device_arch()
+            if cc < 100:
+                raise RuntimeError(f"mcvd_b200 kernels are built for sm_100a only (device reports sm_{cc}: "
+                                   f"{lib.last_error()})")
+        self.conv_mode = os.environ.get("MCVD_CONV", "umma").lower()       # 'umma' | 'simt'
+        self.attn_mode = os.environ.get("MCVD_ATTN", "simt").lower()
+        self.packed: Dict[str, object] = {}
+        self.packed_version = None
+        self.programs: Dict[int, Program] = {}
+        self.launches_last_forward = 0
+
+    # ------------------------------------------------------------------------------ weights
+    def _version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+
+    def _sd(self, key):
+        return self._params[key]
+
+    def ensure_packed(self):
+        v = self._version()
+        if self.packed_version == v:
+            return
+        self._params = {k: p.detach() for k, p in self.module.named_parameters()}
+        self.packed = {}
+        self.programs = {}          # programs hold pointers into the packed tensors
+        self.packed_version = v
+        ns = self.spec
+        # timestep-embedding frequencies, exactly as the reference computes them (layers.py:508-511)
+        half = ns.nf // 2
+        e = math.log(10000) / (half - 1)
+        self.packed["freqs"] = torch.exp(torch.arange(half, dtype=torch.float32) * -e).to(self.device)
+        # fused FiLM projection: every Dense_0 of every act-norm stacked into one [film_total, 4nf] matrix
+        ws, bs = [], []
+        for ms in ns.mods:
+            if ms.kind == "res":
+                for an in ("actnorm0", "actnorm1"):
+                    ws.append(self._sd(f"unet.all_modules.{ms.idx}.{an}.Dense_0.weight"))
+                    bs.append(self._sd(f"unet.all_modules.{ms.idx}.{an}.Dense_0.bias"))
+        self.packed["film_w"] = torch.cat(ws, 0).contiguous().float()
+        self.packed["film_b"] = torch.cat(bs, 0).contiguous().float()
+        assert self.packed["film_w"].shape[0] == ns.film_total
+
+    def _conv_taps(self, w: torch.Tensor) -> torch.Tensor:
+        """OIHW -> [taps][I][O] fp32 contiguous."""
+        O, I, kh, kw = w.shape
+        return w.permute(2, 3, 1, 0).reshape(kh * kw, I, O).contiguous().float()
+
+    def _pack_simt(self, taps: torch.Tensor) -> Tuple[torch.Tensor, int]:
+        T, I, O = taps.shape
+        OP = (O + 3) // 4 * 4
+        if OP != O:
+            p = torch.zeros(T, I, OP, device=taps.device, dtype=torch.float32)
+            p[:, :, :O] = taps
+            taps = p
+        return taps.contiguous(), OP
+
+    def _devctx(self):
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+
+    def _pack_umma(self, taps: torch.Tensor, nt: int, kb: int):
+        if self.backend is not None:
+            return self.backend.pack_umma(taps, nt, kb)
+        T, I, O = taps.shape
+        amax = float(taps.abs().max().item())
+        k = 0 if amax == 0.0 else int(math.floor(math.log2(512.0 / amax)))
+        k = max(-24, min(24, k))
+        out = torch.empty(T * I * O * 4, device=taps.device, dtype=torch.uint8)
+        stream = self._stream()
+        with self._devctx():
+            rc = self.lib.mcvd_umma_pack_weights(taps.data_ptr(), T, I, O, nt, kb, out.data_ptr(), k, stream)
+        if rc < 0:
+            raise RuntimeError(f"mcvd_b200 umma_pack_weights failed: {lib.last_error()}")
+        return out, float(2.0 ** (-k))
+
+    # ------------------------------------------------------------------------------ lowering
+    def program(self, B: int) -> Program:
+        self.ensure_packed()
+        if B not in self.programs:
+            with self._devctx():
+                self.programs[B] = self._build(B)
+            if self.backend is not None:
+                self._register_all(self.programs[B])
+        return self.programs[B]
+
+    def _register_all(self, P):
+        def reg(v):
+            if isinstance(v, torch.Tensor):
+                self.backend.register(v)
+            elif isinstance(v, (tuple, list)):
+                for e in v:
+                    reg(e)
+        for t in P.keep:
+            reg(t)
+        for v in self.packed.values():
+            reg(v)
+
+    def _build(self, B: int) -> Program:
+        ns = self.spec
+        dev = self.device
+        P = Program()
+        P.B = B
+        S = ns.image_size
+
+        def f32(*shape):
+            t = torch.empty(shape, device=dev, dtype=torch.float32)
+            P.keep.append(t)
+            return t
+
+        def keep(t):
+            P.keep.append(t)
+            return t
+
+        def emit(ops, kind, **kw):
+            o = McvdOp()
+            o.kind = kind
+            o.B = B
+            for k, v in kw.items():
+                if k in ("src0", "src1", "w", "bias", "aux0", "aux1", "aux2", "dst", "dst2"):
+                    if isinstance(v, torch.Tensor):
+                        v = v.data_ptr()
+                    setattr(o, k, v)
+                else:
+                    setattr(o, k, v)
+            ops.append(o)
+            return o
+
+        sd = self._sd
+        step, cnd = P.step_ops, P.cond_ops
+
+        # ---- convolution (tensor-core or CUDA-core) -------------------------------------------
+        def conv(ops, key, src: Src, H: int, cout: int, ks: int, wname: str, bname: str, residual=None,
+                 scale=1.0, tab=None, act_in=False, act_out=False, nin=False, wcat=None, bcat=None):
+            """dst = scale * (conv(act(norm(src))) + bias + residual)."""
+            if wcat is not None:
+                taps, bias = wcat, bcat
+            elif nin:
+                taps = sd(wname).float().unsqueeze(0).contiguous()          # NIN W[in, out] == [1][I][O]
+                bias = sd(bname).float().contiguous()
+            else:
+                taps = self._conv_taps(sd(wname))
+                bias = sd(bname).float().contiguous()
+            keep(bias)
+            dst = f32(B, H, H, cout)
+            kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
+            nt = _pick_nt(cout) if cout % 16 == 0 else 0
+            if kb and nt:
+                pk = (key, "umma", nt, kb)
+                if pk not in self.packed:
+                    self.packed[pk] = self._pack_umma(taps, nt, kb)
+                wp, wscale = self.packed[pk]
+                pimg = (H + 1) * (H + 1) if ks == 3 else H * H
+                qtot = B * pimg
+                nacc = 2
+                if -(-qtot // 256) * (cout // nt) < 148 and -(-qtot // 128) > -(-qtot // 256):
+                    nacc = 1
+                fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
+                emit(ops, lib.OP_CONV_UMMA, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=nt, i2=nacc,
+                     f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, aux1=tab,
+                     dst=dst, flags=fl)
+                P.n_umma += 1
+                return dst
+            if tab is not None:
+                a = f32(B, H, H, src.C)
+                emit(ops, lib.OP_APPLY, H=H, W=H, C0=src.c0, C1=src.c1, src0=src.t0, src1=src.t1, aux0=tab, dst=a,
+                     flags=lib.F_ACT_OUT if act_in else 0)
+                src = Src(a, src.C)
+            pk = (key, "simt")
+            if pk not in self.packed:
+                self.packed[pk] = self._pack_simt(taps)
+            wp, coutp = self.packed[pk]
+            emit(ops, lib.OP_CONV_SIMT, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=coutp, f0=scale,
+                 src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, dst=dst,
+                 flags=lib.F_ACT_OUT if act_out else 0)
+            P.n_simt += 1
+            return dst
+
+        # ---- GroupNorm statistics -> (mean, rstd, G, S) table -----------------------------------
+        def norm_table(ops, src: Src, H: int, eps: float, film_off=None, affine=None):
+            C = src.C
+            cg = C // arch.num_groups(C)
+            nchunk = max(1, (H * H) // GN_PPC)
+            part = torch.empty(B * nchunk * C * 2, device=dev, dtype=torch.float64)
+            keep(part)
+            tab = f32(B, C, 4)
+            emit(ops, lib.OP_GN_PARTIAL, H=H, W=H, C0=src.c0, C1=src.c1, i0=nchunk, src0=src.t0, src1=src.t1,
+                 dst=part)
+            kw = dict(H=H, W=H, C0=C, i0=nchunk, i1=cg, f0=eps, src0=part, dst=tab)
+            if film_off is not None:
+                kw.update(aux0=P.film, i2=ns.film_total, i3=film_off, flags=lib.F_FILM)
+            elif affine is not None:
+                kw.update(aux0=keep(affine[0].float().contiguous()), aux1=keep(affine[1].float().contiguous()))
+            emit(ops, lib.OP_GN_FINALIZE, **kw)
+            return tab
+
+        # ---- SPADE gamma / beta (cond-only; reference layerspp.py:165-168) -------------------------
+        cond_at: Dict[int, torch.Tensor] = {}
+
+        def cond_resized(H):
+            if H not in cond_at:
+                if H == S:
+                    cond_at[H] = P.cond_nhwc
+                else:
+                    t = f32(B, H, H, ns.cond_ch)
+                    emit(cnd, lib.OP_RESIZE_NEAREST, H=H, W=H, C0=ns.cond_ch, i0=S, i1=S, src0=P.cond_nhwc, dst=t)
+                    cond_at[H] = t
+            return cond_at[H]
+
+        def spade_gb(prefix: str, C: int, H: int):
+            seg = cond_resized(H)
+            a = conv(cnd, prefix + "mlp_shared", Src(seg, ns.cond_ch), H, ns.spade_dim, 3,
+                     prefix + "mlp_shared.0.weight", prefix + "mlp_shared.0.bias", act_out=True)
+            g = conv(cnd, prefix + "mlp_gamma", Src(a, ns.spade_dim), H, C, 3, prefix + "mlp_gamma.weight",
+                     prefix + "mlp_gamma.bias")
+            b = conv(cnd, prefix + "mlp_beta", Src(a, ns.spade_dim), H, C, 3, prefix + "mlp_beta.weight",
+                     prefix + "mlp_beta.bias")
+            return g, b
+
+        # ---- inputs ---------------------------------------------------------------------------------
+        P.x_in = f32(B, ns.out_ch, S, S)
+        P.cond_in = f32(B, ns.cond_ch, S, S) if ns.cond_ch > 0 else None
+        P.t = f32(B)
+        P.out = f32(B, ns.out_ch, S, S)
+        P.eps_nhwc = f32(B, S, S, ns.out_ch)
+        P.noise = f32(B, ns.out_ch, S, S)
+        if ns.spade:
+            P.cond_nhwc = f32(B, S, S, ns.cond_ch)
+            emit(cnd, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.cond_ch, src0=P.cond_in, dst=P.cond_nhwc)
+            xin = f32(B, S, S, ns.in_ch)
+            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, src0=P.x_in, dst=xin)
+        else:
+            xin = f32(B, S, S, ns.in_ch)
+            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, C1=ns.cond_ch, src0=P.x_in, src1=P.cond_in,
+                 dst=xin)
+
+        # ---- time embedding + all FiLM projections (ncsnpp_more.py:273-280; layerspp.py:521) --------
+        mods = ns.mods
+        emb, h0, temb = f32(B, ns.nf), f32(B, ns.temb_dim), f32(B, ns.temb_dim)
+        P.film = f32(B, ns.film_total)
+        emit(step, lib.OP_TIMESTEP_EMBED, Cout=ns.nf, src0=P.t, w=self.packed["freqs"], dst=emb)
+        emit(step, lib.OP_LINEAR, C0=ns.nf, Cout=ns.temb_dim, src0=emb, w=keep(sd("unet.all_modules.0.weight").float().contiguous()),
+             bias=keep(sd("unet.all_modules.0.bias").float().contiguous()), dst=h0, flags=lib.F_ACT_OUT)
+        emit(step, lib.OP_LINEAR, C0=ns.temb_dim, Cout=ns.temb_dim, src0=h0,
+             w=keep(sd("unet.all_modules.1.weight").float().contiguous()),
+             bias=keep(sd("unet.all_modules.1.bias").float().contiguous()), dst=temb, flags=lib.F_ACT_OUT)
+        emit(step, lib.OP_LINEAR, C0=ns.temb_dim, Cout=ns.film_total, src0=temb, w=self.packed["film_w"],
+             bias=self.packed["film_b"], dst=P.film)
+
+        # ---- blocks ---------------------------------------------------------------------------------
+        def resblock(ms: arch.ModSpec, src: Src) -> torch.Tensor:
+            pre = f"unet.all_modules.{ms.idx}."
+            Hin = ms.res
+            H = Hin * 2 if ms.up else (Hin // 2 if ms.down else Hin)
+            Cin, Cout = ms.in_ch, ms.out_ch
+            eps = 1e-6 if ns.spade else 1e-5           # MySPADE param-free GN eps (layerspp.py:131) vs get_norm (:477)
+            tab0 = norm_table(step, src, Hin, eps, film_off=ms.film_off[0])
+            resample = lib.F_UP if ms.up else (lib.F_DOWN if ms.down else 0)
+            sc_src = src
+            if ns.spade or resample:
+                g0 = b0 = None
+                if ns.spade:
+                    g0, b0 = spade_gb(pre + "actnorm0.Norm_0.", Cin, Hin)
+                a0 = f32(B, H, H, Cin)
+                emit(step, lib.OP_APPLY, H=H, W=H, C0=src.c0, C1=src.c1, src0=src.t0, src1=src.t1, aux0=tab0, aux1=g0,
+                     aux2=b0, dst=a0, flags=lib.F_ACT_OUT | resample)
+                if resample:                          # FIR applied to the skip branch too (layerspp.py:600-611)
+                    xs = f32(B, H, H, Cin)
+                    emit(step, lib.OP_APPLY, H=H, W=H, C0=src.c0, C1=src.c1, src0=src.t0, src1=src.t1, dst=xs,
+                         flags=resample)
+                    sc_src = Src(xs, Cin)
+                h = conv(step, pre + "Conv_0", Src(a0, Cin), H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias")
+            else:
+                h = conv(step, pre + "Conv_0", src, H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias", tab=tab0,
+                         act_in=True)
+            tab1 = norm_table(step, Src(h, Cout), H, eps, film_off=ms.film_off[1])
+            if ms.has_shortcut:
+                res = conv(step, pre + "Conv_2", sc_src, H, Cout, 1, pre + "Conv_2.weight", pre + "Conv_2.bias")
+            else:
+                assert src.t1 is None and src.c0 == Cout
+                res = src.t0
+            if ns.spade:
+                g1, b1 = spade_gb(pre + "actnorm1.Norm_0.", Cout, H)
+                a1 = f32(B, H, H, Cout)
+                emit(step, lib.OP_APPLY, H=H, W=H, C0=Cout, src0=h, aux0=tab1, aux1=g1, aux2=b1, dst=a1,
+                     flags=lib.F_ACT_OUT)
+                return conv(step, pre + "Conv_1", Src(a1, Cout), H, Cout, 3, pre + "Conv_1.weight",
+                            pre + "Conv_1.bias", residual=res, scale=INV_SQRT2)
+            return conv(step, pre + "Conv_1", Src(h, Cout), H, Cout, 3, pre + "Conv_1.weight", pre + "Conv_1.bias",
+                        residual=res, scale=INV_SQRT2, tab=tab1, act_in=True)
+
+        def attnblock(ms: arch.ModSpec, x: torch.Tensor) -> torch.Tensor:
+            pre = f"unet.all_modules.{ms.idx}."
+            H, C = ms.res, ms.in_ch
+            tab = norm_table(step, Src(x, C), H, 1e-6,
+                             affine=(sd(pre + "GroupNorm_0.weight"), sd(pre + "GroupNorm_0.bias")))
+            wq = torch.cat([sd(pre + f"NIN_{i}.W").float() for i in range(3)], dim=1).unsqueeze(0).contiguous()
+            bq = torch.cat([sd(pre + f"NIN_{i}.b").float() for i in range(3)], dim=0).contiguous()
+            qkv = conv(step, pre + "qkv", Src(x, C), H, 3 * C, 1, None, None, tab=tab, act_in=False, wcat=wq, bcat=bq)
+            att = f32(B, H, H, C)
+            d = C // ms.heads
+            emit(step, lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d, f0=float(int(d) ** (-0.5)), src0=qkv,
+                 dst=att)
+            return conv(step, pre + "NIN_3", Src(att, C), H, C, 1, pre + "NIN_3.W", pre + "NIN_3.b", residual=x,
+                        scale=INV_SQRT2, nin=True)
+
+        h = conv(step, "first", Src(xin, ns.in_ch), S, ns.nf, 3, "unet.all_modules.2.weight", "unet.all_modules.2.bias")
+        hs: List[Tuple[torch.Tensor, int]] = [(h, ns.nf)]
+        cur, cur_c = h, ns.nf
+        for ms in mods[3:-2]:
+            if ms.kind == "res":
+                if ms.skip_ch:
+                    st, sc = hs.pop()
+                    assert sc == ms.skip_ch and cur_c + sc == ms.in_ch
+                    src = Src(cur, cur_c, st, sc)
+                else:
+                    assert cur_c == ms.in_ch
+                    src = Src(cur, cur_c)
+                cur, cur_c = resblock(ms, src), ms.out_ch
+            elif ms.kind == "attn":
+                cur = attnblock(ms, cur)
+            else:
+                raise AssertionError(ms.kind)
+            if ms.push:
+                hs.append((cur, cur_c))
+        assert not hs, "skip stack not empty"
+
+        # ---- final norm + conv (ncsnpp_more.py:375-379) ----------------------------------------------
+        mn, mc = mods[-2], mods[-1]
+        pre = f"unet.all_modules.{mn.idx}."
+        wl = self._conv_taps(sd(f"unet.all_modules.{mc.idx}.weight"))
+        bl = keep(sd(f"unet.all_modules.{mc.idx}.bias").float().contiguous())
+        pk = ("last", "simt")
+        if pk not in self.packed:
+            self.packed[pk] = self._pack_simt(wl)
+        wlp, coutp = self.packed[pk]
+        if ns.spade:
+            tabn = norm_table(step, Src(cur, cur_c), S, 1e-6)
+            gN, bN = spade_gb(pre + "Norm_0.", cur_c, S)
+            an = f32(B, S, S, cur_c)
+            emit(step, lib.OP_APPLY, H=S, W=S, C0=cur_c, src0=cur, aux0=tabn, aux1=gN, aux2=bN, dst=an,
+                 flags=lib.F_ACT_OUT)
+            last_src, tabn = an, None
+        else:
+            tabn = norm_table(step, Src(cur, cur_c), S, 1e-5,
+                              affine=(sd(pre + "Norm_0.weight"), sd(pre + "Norm_0.bias")))
+            last_src = cur
+        if ns.out_ch <= 16 and coutp * 9 * cur_c * 4 <= 200 * 1024:
+            emit(step, lib.OP_CONV_SMALLN, H=S, W=S, C0=cur_c, Cout=ns.out_ch, i1=coutp, src0=last_src, w=wlp, bias=bl,
+                 aux0=tabn, dst=P.eps_nhwc, flags=lib.F_ACT_OUT)
+        else:
+            if tabn is not None:
+                an = f32(B, S, S, cur_c)
+                emit(step, lib.OP_APPLY, H=S, W=S, C0=cur_c, src0=cur, aux0=tabn, dst=an, flags=lib.F_ACT_OUT)
+                last_src = an
+            emit(step, lib.OP_CONV_SIMT, H=S, W=S, C0=cur_c, Cout=ns.out_ch, i0=3, i1=coutp, f0=1.0, src0=last_src,
+                 w=wlp, bias=bl, dst=P.eps_nhwc)
+        P.n_net_ops = len(step)
+
+        P.cond_arr = lib.make_ops(cnd) if cnd else None
+        P.step_arr = lib.make_ops(step)
+        # eps NHWC -> NCHW for the module-level forward()
+        o = McvdOp()
+        o.kind, o.B, o.H, o.W, o.C0 = lib.OP_NHWC_TO_NCHW, B, S, S, ns.out_ch
+        o.src0, o.dst = P.eps_nhwc.data_ptr(), P.out.data_ptr()
+        P.out_arr = lib.make_ops([o])
+        # reverse-diffusion update (coefficients patched per step by the sampler)
+        u = McvdOp()
+        u.kind, u.B, u.H, u.W, u.C0 = lib.OP_DIFFUSION_UPDATE, B, S, S, ns.out_ch
+        u.src0, u.src1, u.dst = P.eps_nhwc.data_ptr(), P.noise.data_ptr(), P.x_in.data_ptr()
+        P.update_arr = lib.make_ops([u])
+        lib.validate_program(P.step_arr, len(step))
+        if cnd:
+            lib.validate_program(P.cond_arr, len(cnd))
+        return P
+
+    # ------------------------------------------------------------------------------ execution
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+
+    def _run(self, arr, n):
+        if self.backend is not None:
+            self.backend.run(arr, n)
+        else:
+            lib.run_program(arr, n, self._stream())
+
+    def run_cond(self, P: Program):
+        if P.cond_arr is not None:
+            self._run(P.cond_arr, len(P.cond_ops))
+
+    def run_step(self, P: Program):
+        self._run(P.step_arr, len(P.step_ops))
+
+    def set_inputs(self, P: Program, x=None, t=None, cond=None):
+        if x is not None:
+            P.x_in.copy_(x.reshape(P.x_in.shape))
+        if t is not None:
+            if torch.is_tensor(t):
+                P.t.copy_(t.reshape(-1).to(torch.float32))
+            else:
+                P.t.fill_(float(t))
+        if cond is not None and P.cond_in is not None:
+            P.cond_in.copy_(cond.reshape(P.cond_in.shape))
+
+    def forward(self, x, y, cond=None):
+        """One network evaluation with the reference's NCHW interface."""
+        ns = self.spec
+        B = x.shape[0]
+        if ns.cond_ch > 0 and cond is None:
+            raise RuntimeError("mcvd_b200: this network was built with conditioning frames; cond is required")
+        with self._devctx():
+            P = self.program(B)
+            self.set_inputs(P, x.float(), y, cond.float() if cond is not None else None)
+            self.run_cond(P)
+            self.run_step(P)
+            self._run(P.out_arr, 1)
+            self.launches_last_forward = len(P.cond_ops) + len(P.step_ops) + 1
+            return P.out.clone()
