@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the MCVD DDPM-sampling hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (CPU arm: the reference algorithm on host cores)
+
+One "step" = one full reverse-diffusion pass over one batch of clips: L network evaluations + the
+final denoise evaluation + L fused updates (models/__init__.py:207-340 in the reference), i.e. one
+``ddpm_sampler`` call; it produces B * num_frames frames.  Default workload = BASELINE.json configs[1]
+("cfg2": smmnist_DDPM_big5 + ngf=96, batch 64, subsample 100, 64x64x1, concat conditioning).
+Multi-GPU = weak scaling: every rank owns ``batch`` clips (clip-sharded, no data-path collective).
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from mcvd_b200 import configs, detfill  # noqa: E402
+
+METRIC = "frames/sec @100 DDPM steps, SMMNIST 64x64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU (default: the workload's)")
+    ap.add_argument("--subsample", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-psnr", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--conv", default=None, choices=[None, "umma", "simt"])
+    ap.add_argument("--cpu-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ flops
+def algorithmic_gflop_per_forward(cfg) -> float:
+    """conv + matmul FLOPs (2 per MAC) of ONE sample-forward on the reference graph."""
+    from mcvd_b200 import arch
+    ns = arch.build_spec(cfg)
+    S = ns.image_size
+    fl = 0.0
+
+    def conv(cin, cout, r, k):
+        return 2.0 * cin * cout * k * k * r * r
+
+    fl += 2.0 * (ns.nf * ns.temb_dim + ns.temb_dim * ns.temb_dim)
+    n_norms = 0
+    for ms in ns.mods:
+        if ms.kind == "conv3x3":
+            fl += conv(ms.in_ch, ms.out_ch, ms.res, 3)
+        elif ms.kind == "res":
+            r_out = ms.res * 2 if ms.up else (ms.res // 2 if ms.down else ms.res)
+            fl += conv(ms.in_ch, ms.out_ch, r_out, 3) + conv(ms.out_ch, ms.out_ch, r_out, 3)
+            if ms.has_shortcut:
+                fl += conv(ms.in_ch, ms.out_ch, r_out, 1)
+            fl += 2.0 * ns.temb_dim * (2 * ms.in_ch + 2 * ms.out_ch)
+            if ns.spade:
+                for ch, r in ((ms.in_ch, ms.res), (ms.out_ch, r_out)):
+                    fl += conv(ns.cond_ch, ns.spade_dim, r, 3) + 2 * conv(ns.spade_dim, ch, r, 3)
+        elif ms.kind == "attn":
+            T, C = ms.res * ms.res, ms.in_ch
+            fl += 4 * 2.0 * C * C * T + 2 * 2.0 * T * T * C
+        elif ms.kind == "norm" and ns.spade:
+            fl += conv(ns.cond_ch, ns.spade_dim, S, 3) + 2 * conv(ns.spade_dim, ms.in_ch, S, 3)
+    return fl / 1e9
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_forward_rate(cfg, sd, B_cpu, n_fwd=2):
+    """frames/s of the reference algorithm (oracle port) on the host cores, from timed forwards."""
+    from oracle import mcvd_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, cond = detfill.synthetic_inputs(cfg, B_cpu)
+    t = torch.full((B_cpu,), 500, dtype=torch.long)
+    O.unet_forward(cfg, sd, x, t, cond)                    # warm-up
+    t0 = time.perf_counter()
+    for _ in range(n_fwd):
+        O.unet_forward(cfg, sd, x, t, cond)
+    dt = (time.perf_counter() - t0) / n_fwd
+    L = cfg.sampling.subsample
+    frames = B_cpu * cfg.data.num_frames
+    return frames / (dt * (L + 1)), dt
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from tests.common import make_module
+    _, net, sd = make_module(args.workload, "cpu")
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_forward_rate(cfg, sd, args.cpu_batch, n_fwd=1)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = statistics.mean(x[0] for x in vals)
+    dt = statistics.mean(x[1] for x in vals)
+    L = cfg.sampling.subsample
+    sample = (f"each step = 1 forward of the oracle port at batch {args.cpu_batch} ({dt:.2f} s), "
+              f"extrapolated x{L + 1} network calls per {args.cpu_batch * cfg.data.num_frames} frames")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * (L + 1) * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {describe(cfg)}", "cpu_batch": args.cpu_batch},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def describe(cfg):
+    d, m = cfg.data, cfg.model
+    return (f"{d.image_size}x{d.image_size}x{d.channels}, frames {d.num_frames}+{d.num_frames_cond} cond, ngf {m.ngf}, "
+            f"ch_mult {list(m.ch_mult)}, {'SPADE' if getattr(m, 'spade', False) else 'concat'} conditioning, "
+            f"DDPM subsample {cfg.sampling.subsample}")
+
+
+# ------------------------------------------------------------------------------------------------ main
+def main():
+    args = parse()
+    cfg = configs.workload(args.workload)
+    if args.subsample:
+        cfg.sampling.subsample = args.subsample
+    if args.impl == "reference":
+        return run_reference_arm(args, cfg)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.conv:
+        os.environ["MCVD_CONV"] = args.conv
+
+    from tests.common import make_module
+    from mcvd_b200 import samplers, runner, lib
+    cfg, net, sd = make_module(args.workload, dev)
+    if args.subsample:
+        cfg.sampling.subsample = args.subsample
+    B = args.batch or cfg.bench_batch
+    L = cfg.sampling.subsample
+    F = cfg.data.num_frames
+    lo = rank * B                                            # global clip offset of this rank (weak scaling)
+    x_all, cond_all = detfill.synthetic_inputs(cfg, B)       # per-rank clips (same synthetic clips per rank)
+    x_host, cond_host = x_all.pin_memory(), cond_all.pin_memory()
+    x_dev, cond_dev = x_host.to(dev), cond_host.to(dev)
+    out_host = torch.empty_like(x_host).pin_memory()
+    kw = dict(final_only=True, denoise=True, subsample_steps=L, clip_before=True, verbose=False, log=False)
+
+    def step_resident(i):
+        return samplers.ddpm_sampler(x_dev, net, cond=cond_dev, philox_seed=1234 + i, clip_offset=lo, **kw)
+
+    def step_e2e(i):
+        xd = x_host.to(dev, non_blocking=True)
+        cd = cond_host.to(dev, non_blocking=True)
+        gen = samplers.ddpm_sampler(xd, net, cond=cd, philox_seed=1234 + i, clip_offset=lo, **kw)[-1]
+        out_host.copy_(gen.reshape(out_host.shape), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return runner.inverse_data_transform(cfg, out_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, K):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    for i in range(args.warmup):
+        step_resident(i)
+    launches_per_step = samplers.ddpm_sampler.last_launches
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms = timed(step_resident, args.steps)
+    clk = clocks.stop()
+    frames_per_step = B * F * world
+    value = frames_per_step * args.steps / (ms / 1e3)
+    for i in range(min(args.warmup, 1)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_val = frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    gf = algorithmic_gflop_per_forward(cfg)
+    pk, pk_src = peaks()
+    P = net.engine().program(B)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split on tcgen05, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {describe(cfg)}", "clips_per_gpu": B, "global_clips": B * world,
+                   "parallelism": f"clip-sharded x{world}, no data-path collective",
+                   "l2": "working set (weights 4x%.0f MB + GBs of activations per forward) exceeds the 126 MB L2; no flush needed"
+                         % (sum(p.numel() for p in net.parameters()) / 1e6),
+                   "conv_backend": net.engine().conv_mode, "noise": "in-kernel Philox4x32-10 keyed by global clip id"},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": (x_host.numel() + cond_host.numel()) * 4 * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 * world},
+        "gpu_launches": int(launches_per_step * args.steps),
+        "clocks": clk,
+        "flops": {"algorithmic_gflop_per_sample_forward": gf,
+                  "algorithmic_tflop_per_frame": gf * (L + 1) / F / 1e3,
+                  "whole_path_achieved_tflops": value * gf * (L + 1) / F / 1e3 / world,
+                  "whole_path_frac_of_bf16_peak": value * gf * (L + 1) / F / 1e3 / world / pk["bf16_tflops_sustained"],
+                  "note": "tensor work executed = 3x algorithmic (fp16 hi/lo split for fp32 parity)"},
+    }
+
+    if rank == 0 and not args.no_roofline:
+        line["roofline"] = roofline(net, P, B, cfg, pk, pk_src)
+    if rank == 0 and world == 1 and not args.no_psnr:
+        line["psnr_vs_oracle_db"] = psnr_check(cfg, net, sd, dev)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_forward_rate(cfg, sd, args.cpu_batch, n_fwd=2)
+        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"2 timed forwards of the oracle port at batch {args.cpu_batch} "
+                                          f"({dt:.2f} s each), extrapolated x{L + 1} calls"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(net, P, B, cfg, pk, pk_src):
+    """Per-op CUDA-event timing of the lowered program (2 forwards after a warm-up one), on the launch
+    stream; the dominant kernel is the tcgen05 implicit-GEMM conv (k_conv_umma)."""
+    from mcvd_b200 import lib
+    eng = net.engine()
+    n = len(P.step_ops)
+    stream = torch.cuda.current_stream().cuda_stream
+    step_ptr = ctypes.cast(P.step_arr, ctypes.POINTER(lib.McvdOp))
+    sz = ctypes.sizeof(lib.McvdOp)
+
+    def op_ptr(i):
+        return ctypes.cast(ctypes.addressof(P.step_arr) + i * sz, ctypes.POINTER(lib.McvdOp))
+
+    eng.run_step(P)
+    torch.cuda.synchronize()
+    reps = 2
+    tot = {}
+    flops_umma = 0.0
+    for rep in range(reps):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        evs[0].record()
+        for i in range(n):
+            lib.check(lib.load().mcvd_run_program(op_ptr(i), 1, ctypes.c_void_p(stream)), "run_program")
+            evs[i + 1].record()
+        torch.cuda.synchronize()
+        for i in range(n):
+            op = P.step_ops[i]
+            ms = evs[i].elapsed_time(evs[i + 1])
+            k = tot.setdefault(op.kind, [0.0, 0])
+            k[0] += ms
+            k[1] += 1
+            if op.kind == lib.OP_CONV_UMMA and rep == 0:
+                flops_umma += 2.0 * op.B * op.H * op.W * (op.C0 + op.C1) * op.Cout * op.i0 * op.i0
+    names = {v: k for k, v in vars(lib).items() if k.startswith("OP_")}
+    per_kind = {names[k][3:].lower(): {"ms_per_forward": v[0] / reps, "launches_per_forward": v[1] // reps}
+                for k, v in sorted(tot.items(), key=lambda kv: -kv[1][0])}
+    total_ms = sum(v[0] for v in tot.values()) / reps
+    out = {"bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"],
+           "peak_source": f"{pk_src} cuBLAS bf16 sustained (MEASURED_PEAKS.json)", "traffic": None,
+           "per_kind": per_kind, "forward_ms_sum_of_kernels": total_ms}
+    if lib.OP_CONV_UMMA in tot:
+        ms_umma = tot[lib.OP_CONV_UMMA][0] / reps
+        ach = flops_umma / (ms_umma / 1e3) / 1e12
+        out.update(kernel="k_conv_umma (tcgen05 implicit-GEMM conv, all conv launches of one forward)",
+                   achieved=ach, frac=ach / pk["bf16_tflops_sustained"], executed_tflops=3 * ach,
+                   executed_frac=3 * ach / pk["bf16_tflops_sustained"],
+                   kernel_share_of_forward=ms_umma / total_ms,
+                   algorithmic_gflop_per_forward_in_kernel=flops_umma / 1e9)
+    else:
+        ms_simt = tot.get(lib.OP_CONV_SIMT, [0.0, 0])[0] / reps
+        out.update(kernel="k_conv_simt", achieved=None, frac=None, kernel_share_of_forward=ms_simt / max(total_ms, 1e-9))
+    return out
+
+
+def psnr_check(cfg, net, sd, dev, B=1):
+    """Full L-step DDPM sampling of one clip with injected noise: CUDA path vs the oracle (CPU)."""
+    from mcvd_b200 import samplers
+    from oracle import mcvd_oracle as O
+    L = cfg.sampling.subsample
+    x, cond = detfill.synthetic_inputs(cfg, B, seed=77)
+    zs = [detfill.normal(f"pz{i}", x.shape, seed=77) for i in range(L - 1)]
+    out = samplers.ddpm_sampler(x.to(dev), net, cond=cond.to(dev), final_only=True, denoise=True, subsample_steps=L,
+                                noise_list=[z.to(dev) for z in zs])[0].cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    fn = lambda xx, tt, cc: O.unet_forward(cfg, sd, xx, tt, cc)
+    ref = O.ddpm_sample(fn, O.make_schedule(cfg), x.clone(), cond, L, True, True, noise=zs)[0]
+    to01 = lambda a: ((a + 1) / 2).clamp(0, 1)
+    return O.psnr01(to01(out), to01(ref))
+
+
+if __name__ == "__main__":
+    main()
