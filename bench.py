@@ -153,7 +153,7 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from tests.common import make_module
+    from mcvd_b200.synthetic import make_module
     _, net, sd = make_module(args.workload, "cpu")
     vals = []
     for i in range(args.warmup + args.steps):
@@ -204,7 +204,7 @@ def main():
     if args.conv:
         os.environ["MCVD_CONV"] = args.conv
 
-    from tests.common import make_module
+    from mcvd_b200.synthetic import make_module
     from mcvd_b200 import samplers, runner, lib
     cfg, net, sd = make_module(args.workload, dev)
     if args.subsample:
