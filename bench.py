@@ -34,6 +34,17 @@ from mcvd_b200 import configs, detfill  # noqa: E402
 METRIC = "frames/sec @100 DDPM steps, SMMNIST 64x64"
 
 
+def log(msg):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def cpu_threads():
+    """Threads for the CPU arm: every host core up to 32 (oneDNN convolutions at batch 1-8 stop scaling
+    and then slow down beyond that on the 128-core GPU hosts; measured with tools/cpu_scaling.py)."""
+    return int(os.environ.get("MCVD_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -48,6 +59,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--conv", default=None, choices=[None, "umma", "simt"])
     ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--psnr-steps", type=int, default=0, help="DDPM steps of the PSNR check (default: the workload's)")
     return ap.parse_args()
 
 
@@ -136,7 +148,7 @@ def peaks():
 def cpu_forward_rate(cfg, sd, B_cpu, n_fwd=2):
     """frames/s of the reference algorithm (oracle port) on the host cores, from timed forwards."""
     from oracle import mcvd_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     x, cond = detfill.synthetic_inputs(cfg, B_cpu)
     t = torch.full((B_cpu,), 500, dtype=torch.long)
     O.unet_forward(cfg, sd, x, t, cond)                    # warm-up
@@ -251,8 +263,11 @@ def main():
         barrier()
         return ms
 
+    log(f"module built; B={B} L={L}; warm-up x{args.warmup}")
     for i in range(args.warmup):
         step_resident(i)
+        torch.cuda.synchronize()
+        log(f"warm-up step {i} done")
     launches_per_step = samplers.ddpm_sampler.last_launches
     clocks = ClockSampler(local)
     clocks.start()
@@ -260,10 +275,12 @@ def main():
     clk = clocks.stop()
     frames_per_step = B * F * world
     value = frames_per_step * args.steps / (ms / 1e3)
+    log(f"resident: {ms / args.steps:.1f} ms/step -> {value:.1f} frames/s")
     for i in range(min(args.warmup, 1)):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps)
     e2e_val = frames_per_step * args.steps / (ms_e2e / 1e3)
+    log(f"e2e: {ms_e2e / args.steps:.1f} ms/step -> {e2e_val:.1f} frames/s")
 
     gf = algorithmic_gflop_per_forward(cfg)
     pk, pk_src = peaks()
@@ -292,8 +309,12 @@ def main():
     if rank == 0 and not args.no_roofline:
         line["roofline"] = roofline(net, P, B, cfg, pk, pk_src)
     if rank == 0 and world == 1 and not args.no_psnr:
-        line["psnr_vs_oracle_db"] = psnr_check(cfg, net, sd, dev)
+        log("PSNR check (CUDA path vs oracle on CPU, 1 clip)")
+        line["psnr_vs_oracle_db"] = psnr_check(cfg, net, sd, dev, steps=args.psnr_steps or L)
+        line["psnr_steps"] = args.psnr_steps or L
+        log(f"psnr {line['psnr_vs_oracle_db']:.1f} dB")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        log("CPU baseline (oracle port)")
         v, dt = cpu_forward_rate(cfg, sd, args.cpu_batch, n_fwd=2)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"2 timed forwards of the oracle port at batch {args.cpu_batch} "
@@ -358,16 +379,16 @@ def roofline(net, P, B, cfg, pk, pk_src):
     return out
 
 
-def psnr_check(cfg, net, sd, dev, B=1):
+def psnr_check(cfg, net, sd, dev, B=1, steps=None):
     """Full L-step DDPM sampling of one clip with injected noise: CUDA path vs the oracle (CPU)."""
     from mcvd_b200 import samplers
     from oracle import mcvd_oracle as O
-    L = cfg.sampling.subsample
+    L = steps or cfg.sampling.subsample
     x, cond = detfill.synthetic_inputs(cfg, B, seed=77)
     zs = [detfill.normal(f"pz{i}", x.shape, seed=77) for i in range(L - 1)]
     out = samplers.ddpm_sampler(x.to(dev), net, cond=cond.to(dev), final_only=True, denoise=True, subsample_steps=L,
                                 noise_list=[z.to(dev) for z in zs])[0].cpu()
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     fn = lambda xx, tt, cc: O.unet_forward(cfg, sd, xx, tt, cc)
     ref = O.ddpm_sample(fn, O.make_schedule(cfg), x.clone(), cond, L, True, True, noise=zs)[0]
     to01 = lambda a: ((a + 1) / 2).clamp(0, 1)

@@ -13,7 +13,7 @@ for s in $STAGES; do
     model_simt) timeout 900 python -m pytest tests/test_gpu_model.py -q -k "simt" > gpurun_out/$s.log 2>&1 ;;
     model_umma) timeout 900 python -m pytest tests/test_gpu_model.py -q -k "not simt" > gpurun_out/$s.log 2>&1 ;;
     smoke)      timeout 600 python __graft_entry__.py --smoke > gpurun_out/$s.log 2>&1 ;;
-    bench)      timeout 1500 python bench.py > gpurun_out/bench.json 2> gpurun_out/$s.log ;;
+    bench)      timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/$s.log ;;
     bench_simt) timeout 1500 python bench.py --conv simt --steps 1 --warmup 1 --no-psnr --no-cpu-baseline > gpurun_out/bench_simt.json 2> gpurun_out/$s.log ;;
     *) echo "unknown stage $s" ;;
   esac
