@@ -40,9 +40,9 @@ def log(msg):
 
 
 def cpu_threads():
-    """Threads for the CPU arm: every host core up to 32 (oneDNN convolutions at batch 1-8 stop scaling
+    """Threads for the CPU arm: every host core up to 16 (oneDNN convolutions at batch 1-8 stop scaling
     and then slow down beyond that on the 128-core GPU hosts; measured with tools/cpu_scaling.py)."""
-    return int(os.environ.get("MCVD_CPU_THREADS", min(os.cpu_count() or 1, 32)))
+    return int(os.environ.get("MCVD_CPU_THREADS", min(os.cpu_count() or 1, 16)))
 
 
 def parse():

@@ -93,6 +93,10 @@ enum {
   MCVD_OP_CONV_SMALLN = 13,
   /* dst[i] = src0[i] (i0 floats) -- device-to-device copy inside a program. */
   MCVD_OP_COPY = 14,
+  /* MCVD_OP_ATTENTION on the tensor cores (tcgen05, fp16 hi/lo split, flash-style online softmax with
+   * S and the per-tile P.V product in TMEM); same fields.  Head dim in {32,48,64,96,128}, H*W a
+   * multiple of the key tile (128, or 64 for head dim 128).  See mcvd_b200/csrc/attention_umma.cu. */
+  MCVD_OP_ATTENTION_UMMA = 15,
   MCVD_OP__COUNT
 };
 

@@ -17,7 +17,7 @@ LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libmcvd_b200.so")
 SOURCES = ["api.cu", "elementwise.cu", "conv_simt.cu", "conv_smalln.cu", "attention_simt.cu", "conv_umma.cu",
            "attention_umma.cu"]
-HEADERS = [os.path.join(CSRC, "mcvd_common.cuh"), os.path.join(os.path.dirname(HERE), "include", "mcvd_b200.h")]
+HEADERS = [os.path.join(CSRC, "mcvd_common.cuh"), os.path.join(CSRC, "umma_ptx.cuh"), os.path.join(os.path.dirname(HERE), "include", "mcvd_b200.h")]
 
 
 def _nvcc() -> str:

@@ -31,6 +31,7 @@ static int dispatch(const McvdOp& op, cudaStream_t s) {
     case MCVD_OP_CONV_UMMA: return launch_conv_umma(op, s);
     case MCVD_OP_CONV_SMALLN: return launch_conv_smalln(op, s);
     case MCVD_OP_COPY: return launch_copy(op, s);
+    case MCVD_OP_ATTENTION_UMMA: return launch_attention_umma(op, s);
     default: break;
   }
   set_error("unknown op kind %d", op.kind);
@@ -80,6 +81,7 @@ static int validate_one(const McvdOp& op, int idx) {
       }
       break;
     case MCVD_OP_ATTENTION:
+    case MCVD_OP_ATTENTION_UMMA:
       if (op.i0 * op.i1 != op.C0) {
         set_error("op %d ATTENTION: heads %d x dim %d != %d", idx, op.i0, op.i1, op.C0);
         return -1;

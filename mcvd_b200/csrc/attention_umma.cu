@@ -1,0 +1,283 @@
+// Multi-head self-attention over the H*W tokens of a sample on the tcgen05 tensor cores, flash style
+// (reference AttnBlockpp.forward, models/better/layerspp.py:239-245: w = softmax_j(q_i.k_j * Ch^-0.5),
+// h_i = sum_j w_ij v_j; the reference materialises w as [B*heads, HW, HW] fp32).
+//
+//   qkv [B, T, 3C] fp32 (q | k | v along channels; head h = channels [h*d, (h+1)*d)),  out [B, T, C]
+//   grid = (ceil(T / 128), heads, B); one CTA owns 128 query rows and walks the keys in tiles of KT.
+//
+// Per key tile:   S = Q K^T   (tcgen05.mma, M=128, N=KT, K=d)          -> TMEM columns [0, KT)
+//                 P = exp(S*scale - m)  by the softmax warps (one thread per query row = TMEM lane:
+//                     no shuffles), written to smem as the A operand of the next MMA
+//                 O_tile = P V (M=128, N=d, K=KT)                       -> TMEM columns [KT, KT+d)
+//                 o = o * exp(m_old - m_new) + O_tile   in registers (d floats per thread)
+// fp32 parity: q, k, v and p are split into fp16 hi + lo and every product is 3 MMAs
+// (hi*hi + lo*hi + hi*lo), fp32 accumulation -- same scheme as conv_umma.cu.
+//
+// Operand layouts (canonical K-major, no swizzle): [k-chunk of 8 halfs][row][16 B], LBO = rows*16,
+// SBO = 128.   V is staged transposed (rows = channels, k = keys) so it is K-major too.
+//
+// Warps: 0-3 softmax / output (thread r <-> query row r <-> TMEM lane r), 4-7 K/V stagers,
+//        8 TMEM allocation + MMA issue.
+#include "mcvd_common.cuh"
+#include "umma_ptx.cuh"
+
+namespace mcvd {
+
+namespace {
+
+using namespace ptx;
+
+constexpr int QT = 128;
+constexpr int ATT_THREADS = 288;
+
+struct AttnArgs {
+  const float* qkv;
+  float* out;
+  int T, C, KT, nkt, tmem_cols;
+  float scale;
+};
+
+// fp32 x8 -> fp16 hi (16 B) + lo (16 B)
+__device__ __forceinline__ void split8(const float v[8], uint4& hv, uint4& lv) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
+    const __half l0 = __float2half_rn(v[2 * e] - __half2float(h0));
+    const __half l1 = __float2half_rn(v[2 * e + 1] - __half2float(h1));
+    hw[e] = pack_half2(h0, h1);
+    lw[e] = pack_half2(l0, l1);
+  }
+  hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+// stage `rows` token rows x D channels (channel-contiguous in global) as a K-major operand
+//   dst[(c8 * rows + r) * 16]  <-  src[(row0 + r) * stride + c8 * 8 .. +8)
+template <int D>
+__device__ __forceinline__ void stage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long stride, int rows,
+                                           int valid_rows, int tid, int nthreads) {
+  const int units = (D / 8) * rows;
+  for (int u = tid; u < units; u += nthreads) {
+    const int c8 = u / rows, r = u - c8 * rows;
+    uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
+    if (r < valid_rows) {
+      const float4* p = reinterpret_cast<const float4*>(src + (long long)r * stride + c8 * 8);
+      const float4 a = __ldg(p), b = __ldg(p + 1);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      split8(v, hv, lv);
+    }
+    const size_t off = ((size_t)c8 * rows + r) * 16;
+    *reinterpret_cast<uint4*>(hi + off) = hv;
+    *reinterpret_cast<uint4*>(lo + off) = lv;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int KT = a.KT;
+  const uint32_t q_half = (D / 8) * QT * 16, k_half = (D / 8) * KT * 16, v_half = (KT / 8) * D * 16,
+                 p_half = (KT / 8) * QT * 16;
+  uint8_t* qh = smem_raw;           uint8_t* ql = qh + q_half;
+  uint8_t* kh = ql + q_half;        uint8_t* kl = kh + k_half;
+  uint8_t* vh = kl + k_half;        uint8_t* vl = vh + v_half;
+  uint8_t* ph = vl + v_half;        uint8_t* pl = ph + p_half;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pl + p_half);
+  const uint32_t bar0 = smem_u32(bars);
+  const uint32_t K_FULL = bar0, V_FULL = bar0 + 8, P_FULL = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
+  const int C3 = 3 * a.C;
+  const float* base = a.qkv + (long long)b * a.T * C3 + h * D;   // q channels of this head, token 0
+
+  if (tid == 0) {
+    mbar_init(K_FULL, 128); mbar_init(V_FULL, 128); mbar_init(P_FULL, 128);
+    mbar_init(S_FULL, 1); mbar_init(O_FULL, 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (tid < 256) stage_rows<D>(qh, ql, base + (long long)q0 * C3, C3, QT, min(QT, a.T - q0), tid, 256);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)KT;
+
+  if (warp < 4) {
+    // ================= softmax + output accumulation: thread r owns query row r =================
+    const int r = tid;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < a.nkt; ++j) {
+      mbar_wait(S_FULL, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = 0; c < KT / 16; ++c) {
+        uint32_t rr[16];
+        tmem_ld16(tS + lane_off + c * 16, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      }
+      // scale > 0, so max(s)*scale == max(s*scale)
+      const float mnew = fmaxf(m, mx * a.scale);
+      const float corr = __expf(m - mnew);
+      float sum = 0.f;
+      for (int c = 0; c < KT / 16; ++c) {
+        uint32_t rr[16];
+        tmem_ld16(tS + lane_off + c * 16, rr);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          p[e] = __expf(fmaf(__uint_as_float(rr[e]), a.scale, -mnew));
+          sum += p[e];
+        }
+        uint4 hv, lv;
+        split8(p, hv, lv);
+        size_t off = ((size_t)(2 * c) * QT + r) * 16;
+        *reinterpret_cast<uint4*>(ph + off) = hv;
+        *reinterpret_cast<uint4*>(pl + off) = lv;
+        split8(p + 8, hv, lv);
+        off = ((size_t)(2 * c + 1) * QT + r) * 16;
+        *reinterpret_cast<uint4*>(ph + off) = hv;
+        *reinterpret_cast<uint4*>(pl + off) = lv;
+      }
+      l = l * corr + sum;
+      m = mnew;
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(P_FULL);
+      mbar_wait(O_FULL, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) {
+        uint32_t rr[16];
+        tmem_ld16(tO + lane_off + c * 16, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) o[c * 16 + e] = fmaf(o[c * 16 + e], corr, __uint_as_float(rr[e]));
+      }
+    }
+    tc_fence_before();
+    if (q0 + r < a.T) {
+      const float inv = 1.0f / l;
+      float* op = a.out + ((long long)b * a.T + q0 + r) * a.C + h * D;
+#pragma unroll
+      for (int c = 0; c < D; c += 4)
+        *reinterpret_cast<float4*>(op + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+    }
+  } else if (warp < 8) {
+    // ================= K / V stagers =================
+    const int st = tid - 128;
+    for (int j = 0; j < a.nkt; ++j) {
+      const int k0 = j * KT;
+      if (j > 0) mbar_wait(S_FULL, (j - 1) & 1);            // S_{j-1} done: K buffer free
+      stage_rows<D>(kh, kl, base + a.C + (long long)k0 * C3, C3, KT, KT, st, 128);
+      fence_proxy_async();
+      mbar_arrive(K_FULL);
+      if (j > 0) mbar_wait(O_FULL, (j - 1) & 1);            // PV_{j-1} done: V buffer free
+      // V^T: rows = channels, k = keys.  unit = (key chunk kc, channel c); lanes walk channels
+      const float* vsrc = base + 2 * a.C + (long long)k0 * C3;
+      for (int u = st; u < (KT / 8) * D; u += 128) {
+        const int kc = u / D, c = u - kc * D;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(vsrc + (long long)(kc * 8 + e) * C3 + c);
+        uint4 hv, lv;
+        split8(v, hv, lv);
+        const size_t off = ((size_t)kc * D + c) * 16;
+        *reinterpret_cast<uint4*>(vh + off) = hv;
+        *reinterpret_cast<uint4*>(vl + off) = lv;
+      }
+      fence_proxy_async();
+      mbar_arrive(V_FULL);
+    }
+  } else if ((tid & 31) == 0) {
+    // ================= MMA issuer =================
+    const uint32_t idesc_s = make_idesc_f16(QT, KT), idesc_o = make_idesc_f16(QT, D);
+    const uint32_t q_lbo = QT * 16, k_lbo = (uint32_t)KT * 16, v_lbo = D * 16, p_lbo = QT * 16;
+    const uint32_t sqh = smem_u32(qh), sql = smem_u32(ql), skh = smem_u32(kh), skl = smem_u32(kl);
+    const uint32_t svh = smem_u32(vh), svl = smem_u32(vl), sph = smem_u32(ph), spl = smem_u32(pl);
+    for (int j = 0; j < a.nkt; ++j) {
+      mbar_wait(K_FULL, j & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ks = 0; ks < D / 16; ++ks) {
+        const uint64_t dqh = make_desc(sqh + 2 * ks * q_lbo, q_lbo, 128), dql = make_desc(sql + 2 * ks * q_lbo, q_lbo, 128);
+        const uint64_t dkh = make_desc(skh + 2 * ks * k_lbo, k_lbo, 128), dkl = make_desc(skl + 2 * ks * k_lbo, k_lbo, 128);
+        umma_f16(tS, dqh, dkh, idesc_s, ks > 0 ? 1u : 0u);
+        umma_f16(tS, dql, dkh, idesc_s, 1u);
+        umma_f16(tS, dqh, dkl, idesc_s, 1u);
+      }
+      umma_commit(S_FULL);
+      mbar_wait(V_FULL, j & 1);
+      mbar_wait(P_FULL, j & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ks = 0; ks < KT / 16; ++ks) {
+        const uint64_t dph = make_desc(sph + 2 * ks * p_lbo, p_lbo, 128), dpl = make_desc(spl + 2 * ks * p_lbo, p_lbo, 128);
+        const uint64_t dvh = make_desc(svh + 2 * ks * v_lbo, v_lbo, 128), dvl = make_desc(svl + 2 * ks * v_lbo, v_lbo, 128);
+        umma_f16(tO, dph, dvh, idesc_o, ks > 0 ? 1u : 0u);
+        umma_f16(tO, dpl, dvh, idesc_o, 1u);
+        umma_f16(tO, dph, dvl, idesc_o, 1u);
+      }
+      umma_commit(O_FULL);
+    }
+  }
+
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  }
+}
+
+template <int D>
+int launch_d(const McvdOp& op, cudaStream_t s) {
+  AttnArgs a;
+  a.qkv = (const float*)op.src0; a.out = (float*)op.dst;
+  a.T = op.H * op.W; a.C = op.C0; a.scale = op.f0;
+  a.KT = (D <= 96) ? 128 : 64;
+  if (a.T < a.KT) a.KT = a.T;
+  MCVD_CHECK(a.KT % 16 == 0 && a.KT >= 16 && a.T % a.KT == 0, "ATTENTION_UMMA: %d tokens not tileable", a.T);
+  a.nkt = a.T / a.KT;
+  int cols = a.KT + D, p2 = 32;
+  while (p2 < cols) p2 <<= 1;
+  a.tmem_cols = p2;
+  const size_t smem = 2 * ((size_t)(D / 8) * QT * 16 + (size_t)(D / 8) * a.KT * 16 + (size_t)(a.KT / 8) * D * 16 +
+                           (size_t)(a.KT / 8) * QT * 16) + 64;
+  MCVD_CHECK(smem <= 227 * 1024, "ATTENTION_UMMA: %zu B of shared memory", smem);
+  cudaError_t e = cudaFuncSetAttribute(k_attention_umma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  MCVD_CHECK(e == cudaSuccess, "ATTENTION_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  dim3 grid(cdiv(a.T, QT), op.i0, op.B);
+  k_attention_umma<D><<<grid, ATT_THREADS, smem, s>>>(a);
+  MCVD_CUDA_LAUNCH_CHECK("attention_umma");
+  return 0;
+}
+
+}  // namespace
+
+int launch_attention_umma(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.dst, "ATTENTION_UMMA: null pointer");
+  MCVD_CHECK(op.i0 * op.i1 == op.C0, "ATTENTION_UMMA: heads %d x dim %d != channels %d", op.i0, op.i1, op.C0);
+  switch (op.i1) {
+    case 32: return launch_d<32>(op, s);
+    case 48: return launch_d<48>(op, s);
+    case 64: return launch_d<64>(op, s);
+    case 96: return launch_d<96>(op, s);
+    case 128: return launch_d<128>(op, s);
+    default: break;
+  }
+  set_error("ATTENTION_UMMA: head dim %d unsupported (32/48/64/96/128)", op.i1);
+  return -1;
+}
+
+}  // namespace mcvd

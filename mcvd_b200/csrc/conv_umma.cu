@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 
 #include "mcvd_common.cuh"
+#include "umma_ptx.cuh"
 
 namespace mcvd {
 
@@ -37,6 +38,7 @@ namespace {
 constexpr int NPROD = 256;      // producer / epilogue threads (8 warps)
 constexpr int NTHREADS = 320;   // + loader warp + MMA warp
 constexpr int MT = 128;         // rows per accumulator (UMMA M)
+constexpr int TAB_NB = 8;       // images whose norm-table rows are staged in smem per K-block
 
 struct UmmaArgs {
   const float* s0;
@@ -57,90 +59,11 @@ struct UmmaArgs {
   int NB;                // weight ring stages
   int tmem_cols;
   int act_in, act_out;
+  int tab_nb;            // images a tile's slab can touch (0: too many for the smem stage -> global reads)
   float wscale, oscale;
 };
 
-// ---- PTX wrappers -----------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t r[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-//   [0,14) start>>4 | [16,30) LBO>>4 (K-direction core-matrix stride) | [32,46) SBO>>4 (8-row group
-//   stride) | [46,48) version = 1 | [61,64) layout = 0 (SWIZZLE_NONE)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
+using namespace ptx;
 
 // position decode: flat q -> pixel index (b*H + y)*W + x, or -1 for padding / out of range
 __device__ __forceinline__ long long decode_pos(const UmmaArgs& a, long long q, int& b_out) {
@@ -154,10 +77,6 @@ __device__ __forceinline__ long long decode_pos(const UmmaArgs& a, long long q, 
     return ((long long)b * a.H + (rr - 1)) * a.W + (cc - 1);
   }
   return ((long long)b * a.H + rr) * a.W + cc;
-}
-
-__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -181,11 +100,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   auto B_EMPTY = [&](int i) { return bar0 + 8u * (4 + a.NB + i); };
   const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * a.NB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + (5 + 2 * a.NB));
+  float4* tab_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][TAB_NB][32]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = a.ks * a.ks;
   const int MTOT = MT * a.NACC;
   const long long p0 = (long long)blockIdx.x * MTOT;   // first output position of this tile
+  // first image touched by the halo slab (positions before 0 clamp to image 0)
+  const long long q_first = p0 - a.halo0;
+  const int tile_b0 = q_first <= 0 ? 0 : (int)min((long long)(a.B - 1), q_first / a.Pimg);
   const int n0 = blockIdx.y * a.NT;
 
   if (tid == 0) {
@@ -209,8 +132,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
 
   if (warp < 8) {
     // =========================== producers ===========================
+    // One thread = one slab position x all KB channels of the K-block: the 128 B (KB=32) channel run of
+    // a pixel is fetched with batched 128-bit loads (full lines, 8 loads in flight per thread), the
+    // (mean, rstd, G, S) rows of the <= TAB_NB images this tile touches are staged in shared memory
+    // once per K-block, and each 8-channel chunk is written as one 16 B hi + one 16 B lo store
+    // (lanes walk positions => conflict-free).
     const int Cin = a.C0 + a.C1;
-    const int units = chunks * a.HP;
+    const bool tab_smem = a.tab != nullptr && a.tab_nb > 0;
     for (int kb = 0; kb < a.nKB; ++kb) {
       const int st = kb & 1;
       mbar_wait(A_EMPTY(st), ((kb >> 1) & 1) ^ 1);
@@ -220,39 +148,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
       uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
       uint8_t* lo_base = hi_base + a_half_bytes;
-      for (int u = tid; u < units; u += NPROD) {
-        const int ch = u / a.HP, h = u - ch * a.HP;
+      float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
+      if (tab_smem) {
+        for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
+          const int bi = i / a.KB, c = i - bi * a.KB;
+          const int b = min(tile_b0 + bi, a.B - 1);
+          tsm[bi * 32 + c] = __ldg(a.tab + (long long)b * Cin + c0 + c);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      for (int h = tid; h < a.HP; h += NPROD) {
         const int2 pi = pinfo[h];
-        uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
         if (pi.x >= 0) {
-          const float* sp = src + (long long)pi.x * cs + cc0 + ch * 8;
-          float4 v0 = *reinterpret_cast<const float4*>(sp);
-          float4 v1 = *reinterpret_cast<const float4*>(sp + 4);
-          float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-          if (a.tab) {
-            const float4* tb = a.tab + (long long)pi.y * Cin + c0 + ch * 8;
+          const float* sp = src + (long long)pi.x * cs + cc0;
+          float4 raw[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float4 t = __ldg(tb + e);
-              float n = ((v[e] - t.x) * t.y) * t.z + t.w;
-              if (a.act_in) n = silu_f(n);
-              v[e] = n;
+          for (int j = 0; j < 8; ++j)
+            if (j < chunks * 2) raw[j] = __ldg(reinterpret_cast<const float4*>(sp) + j);
+          const float4* trow = tab_smem ? (tsm + (pi.y - tile_b0) * 32)
+                                        : (a.tab ? a.tab + (long long)pi.y * Cin + c0 : nullptr);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            if (ch < chunks) {
+              float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
+                            raw[2 * ch + 1].x, raw[2 * ch + 1].y, raw[2 * ch + 1].z, raw[2 * ch + 1].w};
+              if (trow) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float4 t = trow[ch * 8 + e];
+                  float n = ((v[e] - t.x) * t.y) * t.z + t.w;
+                  if (a.act_in) n = n * __frcp_rn(1.0f + __expf(-n));
+                  v[e] = n;
+                }
+              }
+              uint32_t hw[4], lw[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
+                const __half l0 = __float2half_rn(v[2 * e] - __half2float(h0));
+                const __half l1 = __float2half_rn(v[2 * e + 1] - __half2float(h1));
+                hw[e] = pack_half2(h0, h1);
+                lw[e] = pack_half2(l0, l1);
+              }
+              const size_t off = ((size_t)ch * a.HP + h) * 16;
+              *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+              *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
           }
-          __half hh[8], ll[8];
+        } else {
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            hh[e] = __float2half_rn(v[e]);
-            ll[e] = __float2half_rn(v[e] - __half2float(hh[e]));
+          for (int ch = 0; ch < 4; ++ch) {
+            if (ch < chunks) {
+              const size_t off = ((size_t)ch * a.HP + h) * 16;
+              *reinterpret_cast<uint4*>(hi_base + off) = z;
+              *reinterpret_cast<uint4*>(lo_base + off) = z;
+            }
           }
-          hv = make_uint4(pack_half2(hh[0], hh[1]), pack_half2(hh[2], hh[3]), pack_half2(hh[4], hh[5]),
-                          pack_half2(hh[6], hh[7]));
-          lv = make_uint4(pack_half2(ll[0], ll[1]), pack_half2(ll[2], ll[3]), pack_half2(ll[4], ll[5]),
-                          pack_half2(ll[6], ll[7]));
         }
-        const size_t off = ((size_t)ch * a.HP + h) * 16;
-        *reinterpret_cast<uint4*>(hi_base + off) = hv;
-        *reinterpret_cast<uint4*>(lo_base + off) = lv;
       }
       fence_proxy_async();          // make the generic-proxy stores visible to the tensor-core proxy
       mbar_arrive(A_FULL(st));
@@ -321,7 +274,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16 = 0,
       // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(MT >> 4) << 24);
+      const uint32_t idesc = make_idesc_f16(MT, a.NT);
       const uint32_t a_lbo = (uint32_t)a.HP * 16, b_lbo = (uint32_t)a.NT * 16;
       const int ksteps = a.KB / 16;
       int bi = 0;
@@ -436,13 +389,18 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.tmem_cols = p2;
   const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
   const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
-  const size_t fixed = 2 * a_stage + (size_t)a.HP * 8 + 8 * 64 + 16;
+  {
+    int nb = a.HP / a.Pimg + 2;
+    a.tab_nb = (nb <= TAB_NB) ? nb : 0;
+  }
+  const size_t tab_bytes = (size_t)2 * TAB_NB * 32 * 16;
+  const size_t fixed = 2 * a_stage + (size_t)a.HP * 8 + 256 + tab_bytes;
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);
   if (NB > 8) NB = 8;
   a.NB = NB;
-  const size_t smem = 2 * a_stage + (size_t)NB * b_stage + (size_t)a.HP * 8 + (size_t)(5 + 2 * NB) * 8 + 16;
+  const size_t smem = 2 * a_stage + (size_t)NB * b_stage + (size_t)a.HP * 8 + 256 + tab_bytes;
   cudaError_t e = cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
   MCVD_CHECK(e == cudaSuccess, "CONV_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   long long tiles = (a.Qtot + MTOT - 1) / MTOT;

@@ -47,5 +47,6 @@ int launch_diffusion_update(const McvdOp& op, cudaStream_t s);
 int launch_conv_umma(const McvdOp& op, cudaStream_t s);
 int launch_conv_smalln(const McvdOp& op, cudaStream_t s);
 int launch_copy(const McvdOp& op, cudaStream_t s);
+int launch_attention_umma(const McvdOp& op, cudaStream_t s);
 
 }  // namespace mcvd

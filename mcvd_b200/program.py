@@ -63,6 +63,9 @@ class Program:
         self.update_arr = None
         self.n_umma = 0
         self.n_simt = 0
+        self.temb_idx: List[int] = []        # step ops of the time-embedding MLP + fused FiLM projection
+        self.film_fin_idx: List[int] = []    # GN_FINALIZE ops that read the FiLM table
+        self.uniform_t = False
 
 
 class Engine:
@@ -84,7 +87,7 @@ class Engine:
                 raise RuntimeError(f"mcvd_b200 kernels are built for sm_100a only (device reports sm_{cc}: "
                                    f"{lib.last_error()})")
         self.conv_mode = os.environ.get("MCVD_CONV", "umma").lower()       # 'umma' | 'simt'
-        self.attn_mode = os.environ.get("MCVD_ATTN", "simt").lower()
+        self.attn_mode = os.environ.get("MCVD_ATTN", "umma").lower()        # 'umma' | 'simt'
         self.packed: Dict[str, object] = {}
         self.packed_version = None
         self.programs: Dict[int, Program] = {}
@@ -268,6 +271,8 @@ class Engine:
             kw = dict(H=H, W=H, C0=C, i0=nchunk, i1=cg, f0=eps, src0=part, dst=tab)
             if film_off is not None:
                 kw.update(aux0=P.film, i2=ns.film_total, i3=film_off, flags=lib.F_FILM)
+                if ops is step:
+                    P.film_fin_idx.append(len(ops))
             elif affine is not None:
                 kw.update(aux0=keep(affine[0].float().contiguous()), aux1=keep(affine[1].float().contiguous()))
             emit(ops, lib.OP_GN_FINALIZE, **kw)
@@ -317,6 +322,7 @@ class Engine:
         mods = ns.mods
         emb, h0, temb = f32(B, ns.nf), f32(B, ns.temb_dim), f32(B, ns.temb_dim)
         P.film = f32(B, ns.film_total)
+        P.temb_idx = list(range(len(step), len(step) + 4))
         emit(step, lib.OP_TIMESTEP_EMBED, Cout=ns.nf, src0=P.t, w=self.packed["freqs"], dst=emb)
         emit(step, lib.OP_LINEAR, C0=ns.nf, Cout=ns.temb_dim, src0=emb, w=keep(sd("unet.all_modules.0.weight").float().contiguous()),
              bias=keep(sd("unet.all_modules.0.bias").float().contiguous()), dst=h0, flags=lib.F_ACT_OUT)
@@ -378,8 +384,11 @@ class Engine:
             qkv = conv(step, pre + "qkv", Src(x, C), H, 3 * C, 1, None, None, tab=tab, act_in=False, wcat=wq, bcat=bq)
             att = f32(B, H, H, C)
             d = C // ms.heads
-            emit(step, lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d, f0=float(int(d) ** (-0.5)), src0=qkv,
-                 dst=att)
+            T = H * H
+            kt = min(T, 128 if d <= 96 else 64)
+            use_tc = self.attn_mode == "umma" and d in (32, 48, 64, 96, 128) and T % kt == 0 and kt % 16 == 0
+            emit(step, lib.OP_ATTENTION_UMMA if use_tc else lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d,
+                 f0=float(int(d) ** (-0.5)), src0=qkv, dst=att)
             return conv(step, pre + "NIN_3", Src(att, C), H, C, 1, pre + "NIN_3.W", pre + "NIN_3.b", residual=x,
                         scale=INV_SQRT2, nin=True)
 
@@ -470,13 +479,27 @@ class Engine:
     def run_step(self, P: Program):
         self._run(P.step_arr, len(P.step_ops))
 
+    def set_uniform_t(self, P: Program, uniform: bool):
+        """All clips share one timestep (every sampler step): evaluate the time-embedding MLP and the fused
+        FiLM projection for ONE row and let every GN_FINALIZE read it with batch stride 0 -- B x fewer
+        FLOPs and bytes for the [B, 4nf] x [4nf, film_total] projection."""
+        if P.uniform_t == uniform:
+            return
+        for i in P.temb_idx:
+            P.step_arr[i].B = 1 if uniform else P.B
+        for i in P.film_fin_idx:
+            P.step_arr[i].i2 = 0 if uniform else self.spec.film_total
+        P.uniform_t = uniform
+
     def set_inputs(self, P: Program, x=None, t=None, cond=None):
         if x is not None:
             P.x_in.copy_(x.reshape(P.x_in.shape))
         if t is not None:
             if torch.is_tensor(t):
+                self.set_uniform_t(P, False)
                 P.t.copy_(t.reshape(-1).to(torch.float32))
             else:
+                self.set_uniform_t(P, True)
                 P.t.fill_(float(t))
         if cond is not None and P.cond_in is not None:
             P.cond_in.copy_(cond.reshape(P.cond_in.shape))

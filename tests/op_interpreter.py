@@ -133,7 +133,10 @@ class Interpreter:
             S = torch.zeros(B, C)
             if op.aux0:
                 if op.flags & lib.F_FILM:
-                    film = self.get(op.aux0, B * op.i2).view(B, op.i2)
+                    if op.i2 == 0:          # batch stride 0: one shared FiLM row (uniform timestep)
+                        film = self.get(op.aux0)[None, :].expand(B, -1)
+                    else:
+                        film = self.get(op.aux0, B * op.i2).view(B, op.i2)
                     G = 1.0 + film[:, op.i3:op.i3 + C]
                     S = film[:, op.i3 + C:op.i3 + 2 * C]
                 else:
@@ -207,7 +210,7 @@ class Interpreter:
             y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1).contiguous(), self.get(op_.bias, op.Cout),
                          padding=1).permute(0, 2, 3, 1)
             self.get(op.dst, y.numel()).copy_(y.reshape(-1))
-        elif k == lib.OP_ATTENTION:
+        elif k in (lib.OP_ATTENTION, lib.OP_ATTENTION_UMMA):
             C, heads, d = op.C0, op.i0, op.i1
             T = H * W
             qkv = self.get(op.src0, B * T * 3 * C).view(B, T, 3, heads, d)

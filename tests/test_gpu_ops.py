@@ -192,7 +192,10 @@ def test_apply_fir(mode, spade):
 
 @pytest.mark.parametrize("B,H,heads,d", [(2, 8, 1, 32), (2, 16, 2, 48), (1, 32, 2, 96), (2, 8, 4, 96), (1, 16, 1, 192),
                                          (2, 16, 2, 64), (1, 16, 1, 128)])
-def test_attention(B, H, heads, d):
+@pytest.mark.parametrize("kind", ["simt", "umma"])
+def test_attention(B, H, heads, d, kind):
+    if kind == "umma" and d not in (32, 48, 64, 96, 128):
+        pytest.skip("tensor-core attention supports head dims 32..128")
     C, T = heads * d, H * H
     qkv = rnd(B, T, 3 * C, seed=4)
     scale = float(int(d) ** (-0.5))
@@ -201,7 +204,8 @@ def test_attention(B, H, heads, d):
     ref = torch.einsum("bhts,bshd->bthd", torch.softmax(s, -1), v.double()).reshape(B, T, C).float()
     qd = qkv.to(DEV)
     out = torch.zeros(B, T, C, device=DEV)
-    run([mk(lib.OP_ATTENTION, B, H=H, W=H, C0=C, i0=heads, i1=d, f0=scale, src0=qd, dst=out)])
+    run([mk(lib.OP_ATTENTION if kind == "simt" else lib.OP_ATTENTION_UMMA, B, H=H, W=H, C0=C, i0=heads, i1=d, f0=scale,
+            src0=qd, dst=out)])
     assert (out.cpu() - ref).abs().max().item() < 2e-5
 
 
