@@ -41,13 +41,7 @@ struct AttnArgs {
 __device__ __forceinline__ void split8(const float v[8], uint4& hv, uint4& lv) {
   uint32_t hw[4], lw[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
-    const __half l0 = __float2half_rn(v[2 * e] - __half2float(h0));
-    const __half l1 = __float2half_rn(v[2 * e + 1] - __half2float(h1));
-    hw[e] = pack_half2(h0, h1);
-    lw[e] = pack_half2(l0, l1);
-  }
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
   hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
@@ -57,20 +51,44 @@ __device__ __forceinline__ void split8(const float v[8], uint4& hv, uint4& lv) {
 template <int D>
 __device__ __forceinline__ void stage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long stride, int rows,
                                            int valid_rows, int tid, int nthreads) {
+  constexpr int U = 4;                                   // units in flight per thread (8 x LDG.128)
   const int units = (D / 8) * rows;
-  for (int u = tid; u < units; u += nthreads) {
-    const int c8 = u / rows, r = u - c8 * rows;
-    uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
-    if (r < valid_rows) {
-      const float4* p = reinterpret_cast<const float4*>(src + (long long)r * stride + c8 * 8);
-      const float4 a = __ldg(p), b = __ldg(p + 1);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-      split8(v, hv, lv);
+  for (int u0 = tid; u0 < units; u0 += nthreads * U) {
+    float4 va[U], vb[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int u = u0 + i * nthreads;
+      const int c8 = u / rows, r = u - c8 * rows;
+      va[i] = vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u < units && r < valid_rows) {
+        const float4* p = reinterpret_cast<const float4*>(src + (long long)r * stride + c8 * 8);
+        va[i] = __ldg(p);
+        vb[i] = __ldg(p + 1);
+      }
     }
-    const size_t off = ((size_t)c8 * rows + r) * 16;
-    *reinterpret_cast<uint4*>(hi + off) = hv;
-    *reinterpret_cast<uint4*>(lo + off) = lv;
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int u = u0 + i * nthreads;
+      if (u < units) {
+        const int c8 = u / rows, r = u - c8 * rows;
+        const float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+        uint4 hv, lv;
+        split8(v, hv, lv);
+        const size_t off = ((size_t)c8 * rows + r) * 16;
+        *reinterpret_cast<uint4*>(hi + off) = hv;
+        *reinterpret_cast<uint4*>(lo + off) = lv;
+      }
+    }
   }
+}
+
+// 64 consecutive TMEM columns of this thread's lane -> registers (one wait)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t r[64]) {
+  tmem_ld16(taddr, r);
+  tmem_ld16(taddr + 16, r + 16);
+  tmem_ld16(taddr + 32, r + 32);
+  tmem_ld16(taddr + 48, r + 48);
+  tmem_ld_wait();
 }
 
 template <int D>
@@ -119,36 +137,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       mbar_wait(S_FULL, j & 1);
       tc_fence_after();
       float mx = -INFINITY;
-      for (int c = 0; c < KT / 16; ++c) {
-        uint32_t rr[16];
-        tmem_ld16(tS + lane_off + c * 16, rr);
-        tmem_ld_wait();
+      for (int c = 0; c < KT / 64; ++c) {
+        uint32_t rr[64];
+        tmem_ld64(tS + lane_off + c * 64, rr);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
       }
       // scale > 0, so max(s)*scale == max(s*scale)
       const float mnew = fmaxf(m, mx * a.scale);
       const float corr = __expf(m - mnew);
       float sum = 0.f;
-      for (int c = 0; c < KT / 16; ++c) {
-        uint32_t rr[16];
-        tmem_ld16(tS + lane_off + c * 16, rr);
-        tmem_ld_wait();
-        float p[16];
+      for (int c = 0; c < KT / 64; ++c) {
+        uint32_t rr[64];
+        tmem_ld64(tS + lane_off + c * 64, rr);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          p[e] = __expf(fmaf(__uint_as_float(rr[e]), a.scale, -mnew));
-          sum += p[e];
+        for (int g = 0; g < 8; ++g) {
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            p[e] = __expf(fmaf(__uint_as_float(rr[g * 8 + e]), a.scale, -mnew));
+            sum += p[e];
+          }
+          uint4 hv, lv;
+          split8(p, hv, lv);
+          const size_t off = ((size_t)(c * 8 + g) * QT + r) * 16;
+          *reinterpret_cast<uint4*>(ph + off) = hv;
+          *reinterpret_cast<uint4*>(pl + off) = lv;
         }
-        uint4 hv, lv;
-        split8(p, hv, lv);
-        size_t off = ((size_t)(2 * c) * QT + r) * 16;
-        *reinterpret_cast<uint4*>(ph + off) = hv;
-        *reinterpret_cast<uint4*>(pl + off) = lv;
-        split8(p + 8, hv, lv);
-        off = ((size_t)(2 * c + 1) * QT + r) * 16;
-        *reinterpret_cast<uint4*>(ph + off) = hv;
-        *reinterpret_cast<uint4*>(pl + off) = lv;
       }
       l = l * corr + sum;
       m = mnew;
@@ -157,13 +172,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       mbar_arrive(P_FULL);
       mbar_wait(O_FULL, j & 1);
       tc_fence_after();
+      {
+        constexpr int G = (D % 32 == 0) ? 32 : 16;        // columns per wait
 #pragma unroll
-      for (int c = 0; c < D / 16; ++c) {
-        uint32_t rr[16];
-        tmem_ld16(tO + lane_off + c * 16, rr);
-        tmem_ld_wait();
+        for (int c = 0; c < D / G; ++c) {
+          uint32_t rr[G];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[c * 16 + e] = fmaf(o[c * 16 + e], corr, __uint_as_float(rr[e]));
+          for (int q = 0; q < G / 16; ++q) tmem_ld16(tO + lane_off + c * G + q * 16, rr + q * 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < G; ++e) o[c * G + e] = fmaf(o[c * G + e], corr, __uint_as_float(rr[e]));
+        }
       }
     }
     tc_fence_before();
@@ -186,22 +205,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       if (j > 0) mbar_wait(O_FULL, (j - 1) & 1);            // PV_{j-1} done: V buffer free
       // V^T: rows = channels, k = keys.  unit = (key chunk kc, channel c); lanes walk channels
       const float* vsrc = base + 2 * a.C + (long long)k0 * C3;
-      for (int u = st; u < (KT / 8) * D; u += 128) {
-        const int kc = u / D, c = u - kc * D;
-        float v[8];
+      for (int u0 = st; u0 < (KT / 8) * D; u0 += 256) {
+        float v[2][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = __ldg(vsrc + (long long)(kc * 8 + e) * C3 + c);
-        uint4 hv, lv;
-        split8(v, hv, lv);
-        const size_t off = ((size_t)kc * D + c) * 16;
-        *reinterpret_cast<uint4*>(vh + off) = hv;
-        *reinterpret_cast<uint4*>(vl + off) = lv;
+        for (int i = 0; i < 2; ++i) {
+          const int u = u0 + i * 128;
+          const int kc = u / D, c = u - kc * D;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[i][e] = (u < (KT / 8) * D) ? __ldg(vsrc + (long long)(kc * 8 + e) * C3 + c) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int u = u0 + i * 128;
+          if (u < (KT / 8) * D) {
+            const int kc = u / D, c = u - kc * D;
+            uint4 hv, lv;
+            split8(v[i], hv, lv);
+            const size_t off = ((size_t)kc * D + c) * 16;
+            *reinterpret_cast<uint4*>(vh + off) = hv;
+            *reinterpret_cast<uint4*>(vl + off) = lv;
+          }
+        }
       }
       fence_proxy_async();
       mbar_arrive(V_FULL);
     }
-  } else if ((tid & 31) == 0) {
-    // ================= MMA issuer =================
+  } else if (elect_one()) {
+    // ================= MMA issuer (one elected lane of warp 8) =================
     const uint32_t idesc_s = make_idesc_f16(QT, KT), idesc_o = make_idesc_f16(QT, D);
     const uint32_t q_lbo = QT * 16, k_lbo = (uint32_t)KT * 16, v_lbo = D * 16, p_lbo = QT * 16;
     const uint32_t sqh = smem_u32(qh), sql = smem_u32(ql), skh = smem_u32(kh), skl = smem_u32(kl);

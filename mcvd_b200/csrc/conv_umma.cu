@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     // once per K-block, and each 8-channel chunk is written as one 16 B hi + one 16 B lo store
     // (lanes walk positions => conflict-free).
     const int Cin = a.C0 + a.C1;
-    const bool tab_smem = a.tab != nullptr && a.tab_nb > 0;
+    const bool tab_smem = a.tab != nullptr;
     for (int kb = 0; kb < a.nKB; ++kb) {
       const int st = kb & 1;
       mbar_wait(A_EMPTY(st), ((kb >> 1) & 1) ^ 1);
@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
           const int bi = i / a.KB, c = i - bi * a.KB;
           const int b = min(tile_b0 + bi, a.B - 1);
-          tsm[bi * 32 + c] = __ldg(a.tab + (long long)b * Cin + c0 + c);
+          const float4 t = __ldg(a.tab + (long long)b * Cin + c0 + c);
+          tsm[bi * 32 + c] = make_float4(t.x, t.y * t.z, t.w, 0.f);
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
@@ -165,8 +166,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             if (j < chunks * 2) raw[j] = __ldg(reinterpret_cast<const float4*>(sp) + j);
-          const float4* trow = tab_smem ? (tsm + (pi.y - tile_b0) * 32)
-                                        : (a.tab ? a.tab + (long long)pi.y * Cin + c0 : nullptr);
+          const float4* trow = tab_smem ? (tsm + (pi.y - tile_b0) * 32) : nullptr;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
             if (ch < chunks) {
@@ -175,21 +175,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
               if (trow) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                  const float4 t = trow[ch * 8 + e];
-                  float n = ((v[e] - t.x) * t.y) * t.z + t.w;
-                  if (a.act_in) n = n * __frcp_rn(1.0f + __expf(-n));
+                  const float4 t = trow[ch * 8 + e];          // (mean, rstd*G, S, -)
+                  float n = fmaf(v[e] - t.x, t.y, t.z);
+                  if (a.act_in) n = silu_fast(n);
                   v[e] = n;
                 }
               }
               uint32_t hw[4], lw[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half h0 = __float2half_rn(v[2 * e]), h1 = __float2half_rn(v[2 * e + 1]);
-                const __half l0 = __float2half_rn(v[2 * e] - __half2float(h0));
-                const __half l1 = __float2half_rn(v[2 * e + 1] - __half2float(h1));
-                hw[e] = pack_half2(h0, h1);
-                lw[e] = pack_half2(l0, l1);
-              }
+              for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
               const size_t off = ((size_t)ch * a.HP + h) * 16;
               *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
               *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
@@ -257,61 +251,67 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     tc_fence_before();
   } else if (warp == 8) {
     // =========================== weight loader ===========================
-    if (lane == 0) {
+    if (elect_one()) {
       const int total = a.nKB * taps;
       const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk) +
                             (size_t)blockIdx.y * (size_t)a.nKB * taps * b_stage_bytes;
+      const uint32_t b0 = smem_u32(b_base);
+      int st = 0, ph = 1;
       for (int i = 0; i < total; ++i) {
-        const int st = i % a.NB;
-        mbar_wait(B_EMPTY(st), ((i / a.NB) & 1) ^ 1);
+        mbar_wait(B_EMPTY(st), ph);
         mbar_arrive_expect_tx(B_FULL(st), b_stage_bytes);
-        bulk_g2s(smem_u32(b_base + (size_t)st * b_stage_bytes), wsrc + (size_t)i * b_stage_bytes, b_stage_bytes,
-                 B_FULL(st));
+        bulk_g2s(b0 + (uint32_t)st * b_stage_bytes, wsrc + (size_t)i * b_stage_bytes, b_stage_bytes, B_FULL(st));
+        if (++st == a.NB) { st = 0; ph ^= 1; }
       }
     }
   } else {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16 = 0,
-      // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(MT, a.NT);
-      const uint32_t a_lbo = (uint32_t)a.HP * 16, b_lbo = (uint32_t)a.NT * 16;
+      const uint32_t a_lbo16 = (uint32_t)a.HP, b_lbo16 = (uint32_t)a.NT;      // LBO in 16-byte units
+      const uint64_t a_proto = make_desc(0, a_lbo16 * 16, 128), b_proto = make_desc(0, b_lbo16 * 16, 128);
       const int ksteps = a.KB / 16;
-      int bi = 0;
+      const uint32_t a_half16 = a_half_bytes >> 4, b_step16 = b_step_bytes >> 4, b_lo16 = 2u * a.NT;
+      const uint32_t a0_16 = smem_u32(a_base) >> 4, b0_16 = smem_u32(b_base) >> 4;
+      const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
+      int bst = 0, bph = 0;
+      uint32_t accum = 0;                      // 0 only for the very first MMA of each accumulator
       for (int kb = 0; kb < a.nKB; ++kb) {
         const int st = kb & 1;
         mbar_wait(A_FULL(st), (kb >> 1) & 1);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_base + (size_t)st * a_stage_bytes);
-        const uint32_t a_lo = a_hi + a_half_bytes;
-        for (int tap = 0; tap < taps; ++tap, ++bi) {
-          const int bst = bi % a.NB;
-          mbar_wait(B_FULL(bst), (bi / a.NB) & 1);
+        const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
+        for (int tap = 0; tap < taps; ++tap) {
+          mbar_wait(B_FULL(bst), bph);
           tc_fence_after();
           const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
-          const uint32_t b_stage = smem_u32(b_base + (size_t)bst * b_stage_bytes);
+          const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
+          const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
           for (int s = 0; s < ksteps; ++s) {
-            const uint32_t b_hi = b_stage + (uint32_t)s * b_step_bytes;
-            const uint32_t b_lo = b_hi + 32u * a.NT;
-            const uint64_t dbh = make_desc(b_hi, b_lbo, 128);
-            const uint64_t dbl = make_desc(b_lo, b_lbo, 128);
-            for (int acc = 0; acc < a.NACC; ++acc) {
-              const uint32_t row_off = (uint32_t)((a.halo0 + shift + acc * MT) * 16) + (uint32_t)(s * 2) * a_lbo;
-              const uint64_t dah = make_desc(a_hi + row_off, a_lbo, 128);
-              const uint64_t dal = make_desc(a_lo + row_off, a_lbo, 128);
-              const uint32_t d = tmem_base + (uint32_t)(acc * a.NT);
-              const uint32_t first = (kb == 0 && tap == 0 && s == 0) ? 0u : 1u;
-              umma_f16(d, dah, dbh, idesc, first);
-              umma_f16(d, dal, dbh, idesc, 1u);
-              umma_f16(d, dah, dbl, idesc, 1u);
+            const uint64_t dbh = desc_add(b_proto, b_tap16 + (uint32_t)s * b_step16);
+            const uint64_t dbl = desc_add(dbh, b_lo16);
+            const uint32_t a_s16 = a_tap16 + (uint32_t)(2 * s) * a_lbo16;
+#pragma unroll
+            for (int acc = 0; acc < 2; ++acc) {
+              if (acc < a.NACC) {
+                const uint64_t dah = desc_add(a_proto, a_s16 + (uint32_t)(acc * MT));
+                const uint64_t dal = desc_add(dah, a_half16);
+                const uint32_t d = tmem_base + (uint32_t)(acc * a.NT);
+                umma_f16(d, dah, dbh, idesc, accum);
+                umma_f16(d, dal, dbh, idesc, 1u);
+                umma_f16(d, dah, dbl, idesc, 1u);
+              }
             }
+            accum = 1u;
           }
           umma_commit(B_EMPTY(bst));        // weights of this stage consumed
+          if (++bst == a.NB) { bst = 0; bph ^= 1; }
         }
         umma_commit(A_EMPTY(st));           // slab of this K-block consumed
       }
       umma_commit(ACC_FULL);
     }
+    __syncwarp();
   }
 
   __syncthreads();
@@ -391,6 +391,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
   {
     int nb = a.HP / a.Pimg + 2;
+    MCVD_CHECK(nb <= TAB_NB || !a.tab, "CONV_UMMA: %dx%d images are too small for the fused-norm path", op.H, op.W);
     a.tab_nb = (nb <= TAB_NB) ? nb : 0;
   }
   const size_t tab_bytes = (size_t)2 * TAB_NB * 32 * 16;

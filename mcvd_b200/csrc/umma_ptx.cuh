@@ -95,6 +95,39 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
   return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
+// one elected lane of a converged warp (lets the compiler emit straight-line UTCHMMA / UBLKCP code
+// instead of a per-active-thread ELECT loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// descriptor with the start-address field advanced by `units16` (16-byte units); fields do not overlap
+__device__ __forceinline__ uint64_t desc_add(uint64_t d, uint32_t units16) { return d + (uint64_t)units16; }
+
+// ---- cheap math for the operand producers ------------------------------------------------------
+// SiLU with the approximate SFU ops (ex2.approx / rcp.approx, <= 2 ulp each): x / (1 + 2^(-x*log2 e))
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+// two fp32 -> fp16 hi pair + fp16 lo pair (lo = fp16(v - float(hi))); one packed convert per pair
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16 = 0,
 // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {

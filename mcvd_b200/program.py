@@ -227,7 +227,7 @@ class Engine:
             dst = f32(B, H, H, cout)
             kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
             nt = _pick_nt(cout) if cout % 16 == 0 else 0
-            if kb and nt:
+            if kb and nt and (tab is None or H >= 8):      # fused-norm slab stages <= 8 images' table rows
                 pk = (key, "umma", nt, kb)
                 if pk not in self.packed:
                     self.packed[pk] = self._pack_umma(taps, nt, kb)
