@@ -48,6 +48,7 @@ struct UmmaArgs {
   const float* res;
   const float4* tab;     // norm table [B][Cin] (mean, rstd, G, S) or null
   float* dst;
+  long long* dbg;        // optional per-CTA cycle counters (tools/umma_timing.py); null in production
   int B, H, W, C0, C1, Cout;
   int ks;                // 1 or 3
   int Wp, Pimg;          // padded row pitch, positions per image
@@ -59,6 +60,7 @@ struct UmmaArgs {
   int NB;                // weight ring stages
   int tmem_cols;
   int act_in, act_out;
+  int ab_bytes;          // bytes reserved for the A stages + B ring (also the epilogue transpose pads)
   int tab_nb;            // images a tile's slab can touch (0: too many for the smem stage -> global reads)
   float wscale, oscale;
 };
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   const uint32_t b_stage_bytes = (uint32_t)(a.KB / 16) * b_step_bytes;
   uint8_t* a_base = smem_raw;
   uint8_t* b_base = a_base + 2 * a_stage_bytes;
-  int2* pinfo = reinterpret_cast<int2*>(b_base + (size_t)a.NB * b_stage_bytes);
+  int2* pinfo = reinterpret_cast<int2*>(a_base + a.ab_bytes);   // operand stages (>= 32 KB: epilogue pads)
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pinfo) + (size_t)a.HP * sizeof(int2));
   // bars: a_full[2], a_empty[2], b_full[NB], b_empty[NB], acc_full
   uint32_t bar0 = smem_u32(bars);
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * a.NB);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + (5 + 2 * a.NB));
   float4* tab_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][TAB_NB][32]
+  float* bias_s = reinterpret_cast<float*>(tab_s + 2 * TAB_NB * 32);                    // [NT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = a.ks * a.ks;
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  for (int i = threadIdx.x; i < a.NT; i += NTHREADS) bias_s[i] = a.bias ? a.bias[blockIdx.y * a.NT + i] : 0.f;
   // position table for the halo slab
   for (int h = tid; h < a.HP; h += NTHREADS) {
     int b = 0;
@@ -129,126 +133,172 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const long long t_begin = a.dbg ? clock64() : 0;
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 
   if (warp < 8) {
     // =========================== producers ===========================
-    // One thread = one slab position x all KB channels of the K-block: the 128 B (KB=32) channel run of
-    // a pixel is fetched with batched 128-bit loads (full lines, 8 loads in flight per thread), the
-    // (mean, rstd, G, S) rows of the <= TAB_NB images this tile touches are staged in shared memory
-    // once per K-block, and each 8-channel chunk is written as one 16 B hi + one 16 B lo store
-    // (lanes walk positions => conflict-free).
+    // One thread = one slab position x all KB channels of the K-block.  Per K-block: the 128 B channel
+    // runs of the thread's (<= 2, rarely 3) positions are requested up front with 128-bit loads (16 in
+    // flight per thread) BEFORE waiting for the stage to drain, the (mean, rstd*G, S) rows of the
+    // <= TAB_NB images the tile touches are staged in smem one K-block ahead, and every 8-channel chunk
+    // leaves as one 16 B hi + one 16 B lo store (lanes walk positions => conflict-free).
     const int Cin = a.C0 + a.C1;
-    const bool tab_smem = a.tab != nullptr;
+    const bool has_tab = a.tab != nullptr;
+    int ppix[3], pb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int h = tid + i * NPROD;
+      ppix[i] = -2;                                  // -2: no such slab row, -1: zero padding
+      pb[i] = 0;
+      if (h < a.HP) { const int2 pi = pinfo[h]; ppix[i] = pi.x; pb[i] = pi.y - tile_b0; }
+    }
+    auto stage_table = [&](int kb) {
+      if (!has_tab || kb >= a.nKB) return;
+      float4* tsm = tab_s + (size_t)(kb & 1) * TAB_NB * 32;
+      const int c0 = kb * a.KB;
+      for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
+        const int bi = i / a.KB, c = i - bi * a.KB;
+        const int b = min(tile_b0 + bi, a.B - 1);
+        const float4 t = __ldg(a.tab + (long long)b * Cin + c0 + c);
+        tsm[bi * 32 + c] = make_float4(t.x, t.y * t.z, t.w, 0.f);
+      }
+    };
+    // transform + split + store one position (raw = its KB channels)
+    auto emit = [&](const float4* raw, int pix, int bidx, int h, const float4* tsm, uint8_t* hi_base, uint8_t* lo_base) {
+      if (pix == -2) return;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < chunks) {
+          uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
+          if (pix >= 0) {
+            float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
+                          raw[2 * ch + 1].x, raw[2 * ch + 1].y, raw[2 * ch + 1].z, raw[2 * ch + 1].w};
+            if (has_tab) {
+              const float4* trow = tsm + bidx * 32 + ch * 8;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float4 t = trow[e];                      // (mean, rstd*G, S, -)
+                float n = fmaf(v[e] - t.x, t.y, t.z);
+                if (a.act_in) n = silu_fast(n);
+                v[e] = n;
+              }
+            }
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
+            hv = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            lv = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+          const size_t off = ((size_t)ch * a.HP + h) * 16;
+          *reinterpret_cast<uint4*>(hi_base + off) = hv;
+          *reinterpret_cast<uint4*>(lo_base + off) = lv;
+        }
+      }
+    };
+    auto fetch = [&](float4* raw, int pix, const float* src, int cs, int cc0) {
+      if (pix >= 0) {
+        const float4* sp = reinterpret_cast<const float4*>(src + (long long)pix * cs + cc0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < chunks * 2) raw[j] = __ldg(sp + j);
+      }
+    };
+
+    stage_table(0);
     for (int kb = 0; kb < a.nKB; ++kb) {
       const int st = kb & 1;
-      mbar_wait(A_EMPTY(st), ((kb >> 1) & 1) ^ 1);
+      long long tw0 = dbg ? clock64() : 0;
       const int c0 = kb * a.KB;
       const float* src;
       int cs, cc0;
       if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
+      float4 raw0[8], raw1[8];
+      fetch(raw0, ppix[0], src, cs, cc0);              // requests in flight while we wait below
+      fetch(raw1, ppix[1], src, cs, cc0);
+      mbar_wait(A_EMPTY(st), ((kb >> 1) & 1) ^ 1);
+      if (has_tab) asm volatile("bar.sync 1, 256;" ::: "memory");   // table of this K-block staged by all
+      if (dbg && tid == 0) { long long t = clock64(); dbg[4] += t - tw0; tw0 = t; }
       uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
       uint8_t* lo_base = hi_base + a_half_bytes;
-      float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
-      if (tab_smem) {
-        for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
-          const int bi = i / a.KB, c = i - bi * a.KB;
-          const int b = min(tile_b0 + bi, a.B - 1);
-          const float4 t = __ldg(a.tab + (long long)b * Cin + c0 + c);
-          tsm[bi * 32 + c] = make_float4(t.x, t.y * t.z, t.w, 0.f);
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      for (int h = tid; h < a.HP; h += NPROD) {
-        const int2 pi = pinfo[h];
-        if (pi.x >= 0) {
-          const float* sp = src + (long long)pi.x * cs + cc0;
-          float4 raw[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < chunks * 2) raw[j] = __ldg(reinterpret_cast<const float4*>(sp) + j);
-          const float4* trow = tab_smem ? (tsm + (pi.y - tile_b0) * 32) : nullptr;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            if (ch < chunks) {
-              float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
-                            raw[2 * ch + 1].x, raw[2 * ch + 1].y, raw[2 * ch + 1].z, raw[2 * ch + 1].w};
-              if (trow) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const float4 t = trow[ch * 8 + e];          // (mean, rstd*G, S, -)
-                  float n = fmaf(v[e] - t.x, t.y, t.z);
-                  if (a.act_in) n = silu_fast(n);
-                  v[e] = n;
-                }
-              }
-              uint32_t hw[4], lw[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hw[e], lw[e]);
-              const size_t off = ((size_t)ch * a.HP + h) * 16;
-              *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-              *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            }
-          }
-        } else {
-          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            if (ch < chunks) {
-              const size_t off = ((size_t)ch * a.HP + h) * 16;
-              *reinterpret_cast<uint4*>(hi_base + off) = z;
-              *reinterpret_cast<uint4*>(lo_base + off) = z;
-            }
-          }
-        }
+      const float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
+      emit(raw0, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
+      emit(raw1, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
+      if (a.HP > 2 * NPROD) {                          // 128-wide images: a third slab row for some threads
+        fetch(raw0, ppix[2], src, cs, cc0);
+        emit(raw0, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
       }
       fence_proxy_async();          // make the generic-proxy stores visible to the tensor-core proxy
       mbar_arrive(A_FULL(st));
+      stage_table(kb + 1);          // other buffer; everyone finished reading it before this K-block's bar.sync
+      if (dbg && tid == 0) dbg[5] += clock64() - tw0;
     }
 
     // =========================== epilogue ===========================
+    // TMEM -> registers -> global, 16 columns at a time; the residual of the NEXT chunk is requested
+    // before the current one is finished so its latency is hidden; bias comes from shared memory.
+    long long te0 = dbg ? clock64() : 0;
     mbar_wait(ACC_FULL, 0);
+    if (dbg && tid == 0) { long long t = clock64(); dbg[6] = t - te0; te0 = t; }
     tc_fence_after();
+    // Each warp drains its 32 TMEM lanes (rows) in column blocks of 32 (or a 16-wide tail): the block is
+    // transposed through an XOR-swizzled 4 KB shared-memory pad (the operand stages are dead by now) so
+    // that every global load / store instruction covers whole 128-byte lines of `dst` / `res`
+    // (8 lanes per row) instead of 32 scattered 16-byte pieces.
     const int lq = warp & 3, grp = warp >> 2;
-    const int nchunk = a.NT / 16;
+    float4* pad = reinterpret_cast<float4*>(a_base) + (size_t)warp * 256;     // [32 rows][8 float4]
+    const int nblk = (a.NT + 31) / 32;
+    const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16);
     for (int acc = 0; acc < a.NACC; ++acc) {
-      const long long q = p0 + (long long)acc * MT + lq * 32 + lane;
-      int b = 0;
-      const long long pix = decode_pos(a, q, b);
-      const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(acc * a.NT);
-      for (int j = grp; j < nchunk; j += 2) {
-        uint32_t r[16];
-        tmem_ld16(trow + (uint32_t)(j * 16), r);
+      int bdummy = 0;
+      const long long mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bdummy);
+      const int mypix32 = (int)mypix;
+      for (int blk = grp; blk < nblk; blk += 2) {
+        const int cb = blk * 32;
+        const int w = min(32, a.NT - cb);                 // 32 or 16 columns
+        uint32_t r[32];
+        long long tq0 = dbg ? clock64() : 0;
+        tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb), r);
+        if (w == 32) tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb + 16), r + 16);
         tmem_ld_wait();
-        if (pix >= 0) {
-          const int n = n0 + j * 16;
-          float o[16];
+        if (dbg && tid == 0) { long long t = clock64(); dbg[8] += t - tq0; tq0 = t; }
 #pragma unroll
-          for (int e = 0; e < 16; ++e) o[e] = __uint_as_float(r[e]) * a.wscale;
-          if (a.bias) {
+        for (int q = 0; q < 8; ++q)
+          if (q * 4 < w)
+            pad[lane * 8 + (q ^ (lane & 7))] =
+                make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
+                            __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
+        __syncwarp();
+        if (dbg && tid == 0) { long long t = clock64(); dbg[9] += t - tq0; tq0 = t; }
+        const int lpr = w >> 2;                           // lanes per row (8 or 4)
+        const int rpi = 32 / lpr;                         // rows per instruction (4 or 8)
+        const int q = lane % lpr, rsub = lane / lpr;
+        const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) o[e] += __ldg(a.bias + n + e);
-          }
-          float* dp = a.dst + pix * a.Cout + n;
-          if (a.res) {
-            const float* rp = a.res + pix * a.Cout + n;
-#pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-              float4 rv = *reinterpret_cast<const float4*>(rp + e);
-              o[e] += rv.x; o[e + 1] += rv.y; o[e + 2] += rv.z; o[e + 3] += rv.w;
+        for (int k = 0; k < 8; ++k) {
+          if (k * rpi < 32) {
+            const int row = k * rpi + rsub;
+            const int px = __shfl_sync(0xffffffffu, mypix32, row);
+            if (px >= 0) {
+              float4 v = pad[row * 8 + (q ^ (row & 7))];
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              const long long off = (long long)px * a.Cout + n0 + cb + q * 4;
+              if (a.res) {
+                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.res + off));
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+              }
+              v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
+              if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+              *reinterpret_cast<float4*>(a.dst + off) = v;
             }
           }
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            o[e] *= a.oscale;
-            if (a.act_out) o[e] = silu_f(o[e]);
-          }
-#pragma unroll
-          for (int e = 0; e < 16; e += 4)
-            *reinterpret_cast<float4*>(dp + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
         }
+        __syncwarp();
+        if (dbg && tid == 0) { dbg[10] += clock64() - tq0; dbg[11] += 1; }
       }
     }
     tc_fence_before();
+    if (dbg && tid == 0) { dbg[7] = clock64() - te0; dbg[0] = clock64() - t_begin; }
   } else if (warp == 8) {
     // =========================== weight loader ===========================
     if (elect_one()) {
@@ -278,11 +328,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       uint32_t accum = 0;                      // 0 only for the very first MMA of each accumulator
       for (int kb = 0; kb < a.nKB; ++kb) {
         const int st = kb & 1;
+        long long tm0 = dbg ? clock64() : 0;
         mbar_wait(A_FULL(st), (kb >> 1) & 1);
+        if (dbg) dbg[1] += clock64() - tm0;
         tc_fence_after();
         const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
         for (int tap = 0; tap < taps; ++tap) {
+          long long tb0 = dbg ? clock64() : 0;
           mbar_wait(B_FULL(bst), bph);
+          if (dbg) dbg[2] += clock64() - tb0;
           tc_fence_after();
           const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
           const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
@@ -310,6 +364,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         umma_commit(A_EMPTY(st));           // slab of this K-block consumed
       }
       umma_commit(ACC_FULL);
+      if (dbg) dbg[3] = clock64() - t_begin;
     }
     __syncwarp();
   }
@@ -365,6 +420,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.wpk = (const __half*)op.w;
   a.bias = (const float*)op.bias; a.res = (const float*)op.aux0; a.tab = (const float4*)op.aux1;
   a.dst = (float*)op.dst;
+  a.dbg = (long long*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.Cout = op.Cout; a.ks = op.i0;
   a.NT = op.i1; a.NACC = op.i2;
   a.KB = pick_kb(op.C0, op.C1);
@@ -394,14 +450,17 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
     MCVD_CHECK(nb <= TAB_NB || !a.tab, "CONV_UMMA: %dx%d images are too small for the fused-norm path", op.H, op.W);
     a.tab_nb = (nb <= TAB_NB) ? nb : 0;
   }
-  const size_t tab_bytes = (size_t)2 * TAB_NB * 32 * 16;
+  const size_t tab_bytes = (size_t)2 * TAB_NB * 32 * 16 + 256 * 4;   // norm-table stage + bias
   const size_t fixed = 2 * a_stage + (size_t)a.HP * 8 + 256 + tab_bytes;
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);
   if (NB > 8) NB = 8;
   a.NB = NB;
-  const size_t smem = 2 * a_stage + (size_t)NB * b_stage + (size_t)a.HP * 8 + 256 + tab_bytes;
+  size_t ab = 2 * a_stage + (size_t)NB * b_stage;
+  if (ab < 32768) ab = 32768;
+  a.ab_bytes = (int)ab;
+  const size_t smem = ab + (size_t)a.HP * 8 + 256 + tab_bytes;
   cudaError_t e = cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
   MCVD_CHECK(e == cudaSuccess, "CONV_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   long long tiles = (a.Qtot + MTOT - 1) / MTOT;

@@ -149,3 +149,27 @@ def test_conditioning_and_shard_helpers():
         covered += list(range(lo, hi))
     assert covered == list(range(64))
     assert runner.shard_range(4, 7, 8) == (4, 4)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+def test_patch_shim_installs_and_falls_back_on_cpu():
+    """mcvd_b200.patch swaps get_model / samplers inside the unmodified reference; on a CPU config it
+    must hand back the reference module and the reference samplers' behaviour."""
+    R = ref_import.ref_runner()
+    import models as M
+    from mcvd_b200 import patch
+    orig = (R.get_model, M.ddpm_sampler, M.ddim_sampler, M.FPNDM_sampler)
+    try:
+        patch.install(verbose=False)
+        cfg = configs.workload("tiny")
+        cfg.device = torch.device("cpu")
+        net = R.get_model(cfg)
+        assert type(net).__module__.startswith("models.better"), type(net)
+        net.eval()
+        x, cond = detfill.synthetic_inputs(cfg, 2)
+        z = detfill.normal("z", x.shape)
+        a = M.ddpm_sampler(x.clone(), net, cond=cond, final_only=True, subsample_steps=4, same_noise=True, noise_val=z)
+        b = orig[1](x.clone(), net, cond=cond, final_only=True, subsample_steps=4, same_noise=True, noise_val=z)
+        assert torch.equal(a, b)
+    finally:
+        R.get_model, M.ddpm_sampler, M.ddim_sampler, M.FPNDM_sampler = orig
