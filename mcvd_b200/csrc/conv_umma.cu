@@ -35,8 +35,13 @@ namespace mcvd {
 
 namespace {
 
-constexpr int NPROD = 256;      // producer / epilogue threads (8 warps)
-constexpr int NTHREADS = 320;   // + loader warp + MMA warp
+using namespace ptx;
+
+constexpr int NPROD = 256;      // producer threads (warps 0-7)
+constexpr int W_LOAD = 8;       // weight-loader warp
+constexpr int W_MMA = 9;        // TMEM owner + MMA issuer warp
+constexpr int W_EPI = 10;       // first of the 4 epilogue warps (10..13 -> TMEM lane quadrants 2,3,0,1)
+constexpr int NTHREADS = 448;
 constexpr int MT = 128;         // rows per accumulator (UMMA M)
 constexpr int TAB_NB = 8;       // images whose norm-table rows are staged in smem per K-block
 
@@ -48,43 +53,47 @@ struct UmmaArgs {
   const float* res;
   const float4* tab;     // norm table [B][Cin] (mean, rstd, G, S) or null
   float* dst;
-  long long* dbg;        // optional per-CTA cycle counters (tools/umma_timing.py); null in production
   int B, H, W, C0, C1, Cout;
   int ks;                // 1 or 3
   int Wp, Pimg;          // padded row pitch, positions per image
   long long Qtot;        // total flat positions
-  int NT, NACC, KB;      // n tile, accumulators per CTA, channels per K-block (16|32)
+  int NT, NACC, KB;      // n tile, accumulators per tile, channels per K-block (16|32)
   int HP;                // halo slab positions (multiple of 8)
   int halo0;             // slab index of the tile's first output position
   int nKB;               // K-blocks
   int NB;                // weight ring stages
+  int nsets;             // TMEM accumulator sets (2: epilogue of tile i overlaps the MMAs of tile i+1)
+  int tiles_n, ntiles;   // n tiles per m tile, total tiles
   int tmem_cols;
   int act_in, act_out;
-  int ab_bytes;          // bytes reserved for the A stages + B ring (also the epilogue transpose pads)
-  int tab_nb;            // images a tile's slab can touch (0: too many for the smem stage -> global reads)
+  int tab_nb;            // images a tile's slab can touch
   float wscale, oscale;
 };
 
-using namespace ptx;
-
 // position decode: flat q -> pixel index (b*H + y)*W + x, or -1 for padding / out of range
-__device__ __forceinline__ long long decode_pos(const UmmaArgs& a, long long q, int& b_out) {
+__device__ __forceinline__ int decode_pos(const UmmaArgs& a, long long q, int& b_out) {
   if (q < 0 || q >= a.Qtot) return -1;
-  int b = (int)(q / a.Pimg);
-  int r = (int)(q - (long long)b * a.Pimg);
-  int rr = r / a.Wp, cc = r - rr * a.Wp;
+  const int b = (int)(q / a.Pimg);
+  const int r = (int)(q - (long long)b * a.Pimg);
+  const int rr = r / a.Wp, cc = r - rr * a.Wp;
   b_out = b;
   if (a.ks == 3) {
     if (rr == 0 || cc == 0) return -1;
-    return ((long long)b * a.H + (rr - 1)) * a.W + (cc - 1);
+    return (b * a.H + (rr - 1)) * a.W + (cc - 1);
   }
-  return ((long long)b * a.H + rr) * a.W + cc;
+  return (b * a.H + rr) * a.W + cc;
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------
+// ---- the kernel: persistent CTAs, all phases overlapped ----------------------------------------------
+//   warps 0-7   producers : fp32 NHWC global -> normalise/FiLM/SiLU -> fp16 hi/lo -> smem slab (2 stages)
+//   warp  8     loader    : cp.async.bulk of the pre-packed fp16 hi/lo weight images (ring of NB stages)
+//   warp  9     MMA       : TMEM allocation, single-thread tcgen05.mma issue, commits -> mbarriers
+//   warps 10-13 epilogue  : TMEM -> registers -> swizzled smem transpose -> 128-byte-line global stores
+// A CTA walks tiles blockIdx.x, +gridDim.x, ...; the A/B pipelines run across tile boundaries and the
+// accumulator is double-buffered in TMEM (when 2 * NACC * NT <= 512), so the producers of tile i+1, the
+// MMAs of tile i+1 and the epilogue of tile i all run concurrently, and CTAs drift out of lock-step.
 __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // carve-up: [A stage 0][A stage 1][B ring][pinfo int2[HP]][barriers][tmem slot]
   const int chunks = a.KB / 8;
   const uint32_t a_half_bytes = (uint32_t)chunks * a.HP * 16;       // one of hi / lo
   const uint32_t a_stage_bytes = 2 * a_half_bytes;
@@ -92,79 +101,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   const uint32_t b_stage_bytes = (uint32_t)(a.KB / 16) * b_step_bytes;
   uint8_t* a_base = smem_raw;
   uint8_t* b_base = a_base + 2 * a_stage_bytes;
-  int2* pinfo = reinterpret_cast<int2*>(a_base + a.ab_bytes);   // operand stages (>= 32 KB: epilogue pads)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pinfo) + (size_t)a.HP * sizeof(int2));
-  // bars: a_full[2], a_empty[2], b_full[NB], b_empty[NB], acc_full
-  uint32_t bar0 = smem_u32(bars);
+  float4* pads = reinterpret_cast<float4*>(b_base + (size_t)a.NB * b_stage_bytes);   // 4 warps x [32][8] float4
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pads + 4 * 256);
+  // bars: a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full[NB], b_empty[NB]
+  const uint32_t bar0 = smem_u32(bars);
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };
   auto A_EMPTY = [&](int i) { return bar0 + 8u * (2 + i); };
-  auto B_FULL = [&](int i) { return bar0 + 8u * (4 + i); };
-  auto B_EMPTY = [&](int i) { return bar0 + 8u * (4 + a.NB + i); };
-  const uint32_t ACC_FULL = bar0 + 8u * (4 + 2 * a.NB);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + (5 + 2 * a.NB));
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (4 + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (6 + i); };
+  auto B_FULL = [&](int i) { return bar0 + 8u * (8 + i); };
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (8 + a.NB + i); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   float4* tab_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][TAB_NB][32]
-  float* bias_s = reinterpret_cast<float*>(tab_s + 2 * TAB_NB * 32);                    // [NT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = a.ks * a.ks;
   const int MTOT = MT * a.NACC;
-  const long long p0 = (long long)blockIdx.x * MTOT;   // first output position of this tile
-  // first image touched by the halo slab (positions before 0 clamp to image 0)
-  const long long q_first = p0 - a.halo0;
-  const int tile_b0 = q_first <= 0 ? 0 : (int)min((long long)(a.B - 1), q_first / a.Pimg);
-  const int n0 = blockIdx.y * a.NT;
 
   if (tid == 0) {
-    mbar_init(A_FULL(0), NPROD); mbar_init(A_FULL(1), NPROD);
-    mbar_init(A_EMPTY(0), 1); mbar_init(A_EMPTY(1), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(A_FULL(i), NPROD); mbar_init(A_EMPTY(i), 1);
+      mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128);
+    }
     for (int i = 0; i < a.NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
-    mbar_init(ACC_FULL, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
-  for (int i = threadIdx.x; i < a.NT; i += NTHREADS) bias_s[i] = a.bias ? a.bias[blockIdx.y * a.NT + i] : 0.f;
-  // position table for the halo slab
-  for (int h = tid; h < a.HP; h += NTHREADS) {
-    int b = 0;
-    long long pix = decode_pos(a, p0 - a.halo0 + h, b);
-    pinfo[h] = make_int2((int)pix, b);   // pixel index < 2^31 is checked on the host
-  }
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const long long t_begin = a.dbg ? clock64() : 0;
-  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
 
   if (warp < 8) {
     // =========================== producers ===========================
-    // One thread = one slab position x all KB channels of the K-block.  Per K-block: the 128 B channel
-    // runs of the thread's (<= 2, rarely 3) positions are requested up front with 128-bit loads (16 in
-    // flight per thread) BEFORE waiting for the stage to drain, the (mean, rstd*G, S) rows of the
-    // <= TAB_NB images the tile touches are staged in smem one K-block ahead, and every 8-channel chunk
-    // leaves as one 16 B hi + one 16 B lo store (lanes walk positions => conflict-free).
+    // One thread = one slab position x all KB channels of the K-block.  Per K-block the 128 B channel runs
+    // of the thread's (<= 2, rarely 3) positions are requested up front (16 x LDG.128 in flight) BEFORE
+    // waiting for the stage to drain; the (mean, rstd*G, S) rows of the <= TAB_NB images the tile touches
+    // are staged in smem one K-block ahead; every 8-channel chunk leaves as one 16 B hi + one 16 B lo
+    // store (lanes walk positions => conflict-free).
     const int Cin = a.C0 + a.C1;
     const bool has_tab = a.tab != nullptr;
-    int ppix[3], pb[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int h = tid + i * NPROD;
-      ppix[i] = -2;                                  // -2: no such slab row, -1: zero padding
-      pb[i] = 0;
-      if (h < a.HP) { const int2 pi = pinfo[h]; ppix[i] = pi.x; pb[i] = pi.y - tile_b0; }
-    }
-    auto stage_table = [&](int kb) {
-      if (!has_tab || kb >= a.nKB) return;
-      float4* tsm = tab_s + (size_t)(kb & 1) * TAB_NB * 32;
+    auto tile_b0_of = [&](int t) {
+      const long long q_first = (long long)(t / a.tiles_n) * MTOT - a.halo0;
+      return q_first <= 0 ? 0 : (int)min((long long)(a.B - 1), q_first / a.Pimg);
+    };
+    auto stage_table = [&](int tb0, int kb, int g) {       // table rows of K-block kb -> buffer g & 1
+      if (!has_tab) return;
+      float4* tsm = tab_s + (size_t)(g & 1) * TAB_NB * 32;
       const int c0 = kb * a.KB;
       for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
         const int bi = i / a.KB, c = i - bi * a.KB;
-        const int b = min(tile_b0 + bi, a.B - 1);
+        const int b = min(tb0 + bi, a.B - 1);
         const float4 t = __ldg(a.tab + (long long)b * Cin + c0 + c);
         tsm[bi * 32 + c] = make_float4(t.x, t.y * t.z, t.w, 0.f);
       }
     };
-    // transform + split + store one position (raw = its KB channels)
     auto emit = [&](const float4* raw, int pix, int bidx, int h, const float4* tsm, uint8_t* hi_base, uint8_t* lo_base) {
       if (pix == -2) return;
 #pragma unroll
@@ -205,116 +196,65 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       }
     };
 
-    stage_table(0);
-    for (int kb = 0; kb < a.nKB; ++kb) {
-      const int st = kb & 1;
-      long long tw0 = dbg ? clock64() : 0;
-      const int c0 = kb * a.KB;
-      const float* src;
-      int cs, cc0;
-      if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
-      float4 raw0[8], raw1[8];
-      fetch(raw0, ppix[0], src, cs, cc0);              // requests in flight while we wait below
-      fetch(raw1, ppix[1], src, cs, cc0);
-      mbar_wait(A_EMPTY(st), ((kb >> 1) & 1) ^ 1);
-      if (has_tab) asm volatile("bar.sync 1, 256;" ::: "memory");   // table of this K-block staged by all
-      if (dbg && tid == 0) { long long t = clock64(); dbg[4] += t - tw0; tw0 = t; }
-      uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
-      uint8_t* lo_base = hi_base + a_half_bytes;
-      const float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
-      emit(raw0, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
-      emit(raw1, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
-      if (a.HP > 2 * NPROD) {                          // 128-wide images: a third slab row for some threads
-        fetch(raw0, ppix[2], src, cs, cc0);
-        emit(raw0, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
+    int g = 0;                                             // K-blocks produced so far (all tiles)
+    if ((int)blockIdx.x < a.ntiles) stage_table(tile_b0_of(blockIdx.x), 0, 0);
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+      const long long p0 = (long long)(t / a.tiles_n) * MTOT;
+      const int tb0 = tile_b0_of(t);
+      int ppix[3], pb[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int h = tid + i * NPROD;
+        ppix[i] = -2;                                      // -2: no such slab row, -1: zero padding
+        pb[i] = 0;
+        if (h < a.HP) { int b = tb0; ppix[i] = decode_pos(a, p0 - a.halo0 + h, b); pb[i] = b - tb0; }
       }
-      fence_proxy_async();          // make the generic-proxy stores visible to the tensor-core proxy
-      mbar_arrive(A_FULL(st));
-      stage_table(kb + 1);          // other buffer; everyone finished reading it before this K-block's bar.sync
-      if (dbg && tid == 0) dbg[5] += clock64() - tw0;
-    }
-
-    // =========================== epilogue ===========================
-    // TMEM -> registers -> global, 16 columns at a time; the residual of the NEXT chunk is requested
-    // before the current one is finished so its latency is hidden; bias comes from shared memory.
-    long long te0 = dbg ? clock64() : 0;
-    mbar_wait(ACC_FULL, 0);
-    if (dbg && tid == 0) { long long t = clock64(); dbg[6] = t - te0; te0 = t; }
-    tc_fence_after();
-    // Each warp drains its 32 TMEM lanes (rows) in column blocks of 32 (or a 16-wide tail): the block is
-    // transposed through an XOR-swizzled 4 KB shared-memory pad (the operand stages are dead by now) so
-    // that every global load / store instruction covers whole 128-byte lines of `dst` / `res`
-    // (8 lanes per row) instead of 32 scattered 16-byte pieces.
-    const int lq = warp & 3, grp = warp >> 2;
-    float4* pad = reinterpret_cast<float4*>(a_base) + (size_t)warp * 256;     // [32 rows][8 float4]
-    const int nblk = (a.NT + 31) / 32;
-    const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16);
-    for (int acc = 0; acc < a.NACC; ++acc) {
-      int bdummy = 0;
-      const long long mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bdummy);
-      const int mypix32 = (int)mypix;
-      for (int blk = grp; blk < nblk; blk += 2) {
-        const int cb = blk * 32;
-        const int w = min(32, a.NT - cb);                 // 32 or 16 columns
-        uint32_t r[32];
-        long long tq0 = dbg ? clock64() : 0;
-        tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb), r);
-        if (w == 32) tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb + 16), r + 16);
-        tmem_ld_wait();
-        if (dbg && tid == 0) { long long t = clock64(); dbg[8] += t - tq0; tq0 = t; }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q * 4 < w)
-            pad[lane * 8 + (q ^ (lane & 7))] =
-                make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
-                            __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
-        __syncwarp();
-        if (dbg && tid == 0) { long long t = clock64(); dbg[9] += t - tq0; tq0 = t; }
-        const int lpr = w >> 2;                           // lanes per row (8 or 4)
-        const int rpi = 32 / lpr;                         // rows per instruction (4 or 8)
-        const int q = lane % lpr, rsub = lane / lpr;
-        const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (k * rpi < 32) {
-            const int row = k * rpi + rsub;
-            const int px = __shfl_sync(0xffffffffu, mypix32, row);
-            if (px >= 0) {
-              float4 v = pad[row * 8 + (q ^ (row & 7))];
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              const long long off = (long long)px * a.Cout + n0 + cb + q * 4;
-              if (a.res) {
-                const float4 rv = __ldg(reinterpret_cast<const float4*>(a.res + off));
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              }
-              v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
-              if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-              *reinterpret_cast<float4*>(a.dst + off) = v;
-            }
-          }
+      for (int kb = 0; kb < a.nKB; ++kb, ++g) {
+        const int st = g & 1;
+        const int c0 = kb * a.KB;
+        const float* src;
+        int cs, cc0;
+        if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
+        float4 raw0[8], raw1[8];
+        fetch(raw0, ppix[0], src, cs, cc0);              // requests in flight while we wait below
+        fetch(raw1, ppix[1], src, cs, cc0);
+        mbar_wait(A_EMPTY(st), ((g >> 1) & 1) ^ 1);
+        if (has_tab) asm volatile("bar.sync 1, 256;" ::: "memory");   // this K-block's table staged by all
+        uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
+        uint8_t* lo_base = hi_base + a_half_bytes;
+        const float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
+        emit(raw0, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
+        emit(raw1, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
+        if (a.HP > 2 * NPROD) {                          // 128-wide images: a third slab row for some threads
+          fetch(raw0, ppix[2], src, cs, cc0);
+          emit(raw0, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
         }
-        __syncwarp();
-        if (dbg && tid == 0) { dbg[10] += clock64() - tq0; dbg[11] += 1; }
+        fence_proxy_async();          // make the generic-proxy stores visible to the tensor-core proxy
+        mbar_arrive(A_FULL(st));
+        // table of the NEXT K-block (possibly of the next tile) into the other buffer; everyone finished
+        // reading that buffer before passing this K-block's bar.sync
+        if (kb + 1 < a.nKB) stage_table(tb0, kb + 1, g + 1);
+        else if (t + (int)gridDim.x < a.ntiles) stage_table(tile_b0_of(t + gridDim.x), 0, g + 1);
       }
     }
-    tc_fence_before();
-    if (dbg && tid == 0) { dbg[7] = clock64() - te0; dbg[0] = clock64() - t_begin; }
-  } else if (warp == 8) {
+  } else if (warp == W_LOAD) {
     // =========================== weight loader ===========================
     if (elect_one()) {
-      const int total = a.nKB * taps;
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk) +
-                            (size_t)blockIdx.y * (size_t)a.nKB * taps * b_stage_bytes;
       const uint32_t b0 = smem_u32(b_base);
+      const int per_tile = a.nKB * taps;
       int st = 0, ph = 1;
-      for (int i = 0; i < total; ++i) {
-        mbar_wait(B_EMPTY(st), ph);
-        mbar_arrive_expect_tx(B_FULL(st), b_stage_bytes);
-        bulk_g2s(b0 + (uint32_t)st * b_stage_bytes, wsrc + (size_t)i * b_stage_bytes, b_stage_bytes, B_FULL(st));
-        if (++st == a.NB) { st = 0; ph ^= 1; }
+      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)(t % a.tiles_n) * per_tile * b_stage_bytes;
+        for (int i = 0; i < per_tile; ++i) {
+          mbar_wait(B_EMPTY(st), ph);
+          mbar_arrive_expect_tx(B_FULL(st), b_stage_bytes);
+          bulk_g2s(b0 + (uint32_t)st * b_stage_bytes, wsrc + (size_t)i * b_stage_bytes, b_stage_bytes, B_FULL(st));
+          if (++st == a.NB) { st = 0; ph ^= 1; }
+        }
       }
     }
-  } else {
+    __syncwarp();
+  } else if (warp == W_MMA) {
     // =========================== MMA issuer ===========================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_f16(MT, a.NT);
@@ -324,53 +264,117 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       const uint32_t a_half16 = a_half_bytes >> 4, b_step16 = b_step_bytes >> 4, b_lo16 = 2u * a.NT;
       const uint32_t a0_16 = smem_u32(a_base) >> 4, b0_16 = smem_u32(b_base) >> 4;
       const uint32_t a_stage16 = a_stage_bytes >> 4, b_stage16 = b_stage_bytes >> 4;
-      int bst = 0, bph = 0;
-      uint32_t accum = 0;                      // 0 only for the very first MMA of each accumulator
-      for (int kb = 0; kb < a.nKB; ++kb) {
-        const int st = kb & 1;
-        long long tm0 = dbg ? clock64() : 0;
-        mbar_wait(A_FULL(st), (kb >> 1) & 1);
-        if (dbg) dbg[1] += clock64() - tm0;
+      int bst = 0, bph = 0, g = 0, it = 0;
+      for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+        const int set = it % a.nsets;
+        mbar_wait(ACC_EMPTY(set), ((it / a.nsets) & 1) ^ 1);      // epilogue drained this accumulator set
         tc_fence_after();
-        const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
-        for (int tap = 0; tap < taps; ++tap) {
-          long long tb0 = dbg ? clock64() : 0;
-          mbar_wait(B_FULL(bst), bph);
-          if (dbg) dbg[2] += clock64() - tb0;
+        const uint32_t d0 = tmem_base + (uint32_t)(set * a.NACC * a.NT);
+        uint32_t accum = 0;                    // 0 only for the very first MMA of each accumulator
+        for (int kb = 0; kb < a.nKB; ++kb, ++g) {
+          const int st = g & 1;
+          mbar_wait(A_FULL(st), (g >> 1) & 1);
           tc_fence_after();
-          const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
-          const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
-          const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
-          for (int s = 0; s < ksteps; ++s) {
-            const uint64_t dbh = desc_add(b_proto, b_tap16 + (uint32_t)s * b_step16);
-            const uint64_t dbl = desc_add(dbh, b_lo16);
-            const uint32_t a_s16 = a_tap16 + (uint32_t)(2 * s) * a_lbo16;
+          const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
+          for (int tap = 0; tap < taps; ++tap) {
+            mbar_wait(B_FULL(bst), bph);
+            tc_fence_after();
+            const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
+            const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
+            const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
+            for (int s = 0; s < ksteps; ++s) {
+              const uint64_t dbh = desc_add(b_proto, b_tap16 + (uint32_t)s * b_step16);
+              const uint64_t dbl = desc_add(dbh, b_lo16);
+              const uint32_t a_s16 = a_tap16 + (uint32_t)(2 * s) * a_lbo16;
 #pragma unroll
-            for (int acc = 0; acc < 2; ++acc) {
-              if (acc < a.NACC) {
-                const uint64_t dah = desc_add(a_proto, a_s16 + (uint32_t)(acc * MT));
-                const uint64_t dal = desc_add(dah, a_half16);
-                const uint32_t d = tmem_base + (uint32_t)(acc * a.NT);
-                umma_f16(d, dah, dbh, idesc, accum);
-                umma_f16(d, dal, dbh, idesc, 1u);
-                umma_f16(d, dah, dbl, idesc, 1u);
+              for (int acc = 0; acc < 2; ++acc) {
+                if (acc < a.NACC) {
+                  const uint64_t dah = desc_add(a_proto, a_s16 + (uint32_t)(acc * MT));
+                  const uint64_t dal = desc_add(dah, a_half16);
+                  const uint32_t d = d0 + (uint32_t)(acc * a.NT);
+                  umma_f16(d, dah, dbh, idesc, accum);
+                  umma_f16(d, dal, dbh, idesc, 1u);
+                  umma_f16(d, dah, dbl, idesc, 1u);
+                }
               }
+              accum = 1u;
             }
-            accum = 1u;
+            umma_commit(B_EMPTY(bst));        // weights of this stage consumed
+            if (++bst == a.NB) { bst = 0; bph ^= 1; }
           }
-          umma_commit(B_EMPTY(bst));        // weights of this stage consumed
-          if (++bst == a.NB) { bst = 0; bph ^= 1; }
+          umma_commit(A_EMPTY(st));           // slab of this K-block consumed
         }
-        umma_commit(A_EMPTY(st));           // slab of this K-block consumed
+        umma_commit(ACC_FULL(set));
       }
-      umma_commit(ACC_FULL);
-      if (dbg) dbg[3] = clock64() - t_begin;
     }
     __syncwarp();
+  } else {
+    // =========================== epilogue ===========================
+    // Each of the 4 warps drains its 32 TMEM lanes (rows) in column blocks of 32 (or a 16-wide tail): the
+    // block is transposed through an XOR-swizzled 4 KB shared-memory pad so that every global load / store
+    // instruction covers whole 128-byte lines of `dst` / `res` (8 lanes per row).
+    const int lq = warp & 3;
+    float4* pad = pads + (size_t)(warp - W_EPI) * 256;        // [32 rows][8 float4]
+    const int nblk = (a.NT + 31) / 32;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
+      const int set = it % a.nsets;
+      const long long p0 = (long long)(t / a.tiles_n) * MTOT;
+      const int n0 = (t % a.tiles_n) * a.NT;
+      mbar_wait(ACC_FULL(set), (it / a.nsets) & 1);
+      tc_fence_after();
+      const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(set * a.NACC * a.NT);
+      for (int acc = 0; acc < a.NACC; ++acc) {
+        int bdummy = 0;
+        const int mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bdummy);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const int cb = blk * 32;
+          const int w = min(32, a.NT - cb);                 // 32 or 16 columns
+          uint32_t r[32];
+          tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb), r);
+          if (w == 32) tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb + 16), r + 16);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < w)
+              pad[lane * 8 + (q ^ (lane & 7))] =
+                  make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
+                              __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
+          __syncwarp();
+          const int lpr = w >> 2;                           // lanes per row (8 or 4)
+          const int rpi = 32 / lpr;                         // rows per instruction (4 or 8)
+          const int q = lane % lpr, rsub = lane / lpr;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cb + q * 4));
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k * rpi < 32) {
+              const int row = k * rpi + rsub;
+              const int px = __shfl_sync(0xffffffffu, mypix, row);
+              if (px >= 0) {
+                float4 v = pad[row * 8 + (q ^ (row & 7))];
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                const long long off = (long long)px * a.Cout + n0 + cb + q * 4;
+                if (a.res) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(a.res + off));
+                  v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                }
+                v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
+                if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                *reinterpret_cast<float4*>(a.dst + off) = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(ACC_EMPTY(set));            // 128 arrivals: this accumulator set may be overwritten
+    }
   }
 
   __syncthreads();
-  if (warp == 9) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
@@ -420,51 +424,60 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.wpk = (const __half*)op.w;
   a.bias = (const float*)op.bias; a.res = (const float*)op.aux0; a.tab = (const float4*)op.aux1;
   a.dst = (float*)op.dst;
-  a.dbg = (long long*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.Cout = op.Cout; a.ks = op.i0;
-  a.NT = op.i1; a.NACC = op.i2;
+  a.NT = op.i1;
   a.KB = pick_kb(op.C0, op.C1);
   MCVD_CHECK(a.KB != 0, "CONV_UMMA: input channels (%d,%d) must be multiples of 16", op.C0, op.C1);
   MCVD_CHECK(a.NT >= 16 && a.NT <= 256 && a.NT % 16 == 0 && op.Cout % a.NT == 0,
              "CONV_UMMA: n tile %d invalid for Cout %d", a.NT, op.Cout);
-  MCVD_CHECK(a.NACC == 1 || a.NACC == 2, "CONV_UMMA: accumulators %d", a.NACC);
   if (a.ks == 3) { a.Wp = op.W + 1; a.Pimg = (op.H + 1) * (op.W + 1); }
   else { a.Wp = op.W; a.Pimg = op.H * op.W; }
   a.Qtot = (long long)op.B * a.Pimg;
-  MCVD_CHECK((long long)op.B * op.H * op.W < (1LL << 31), "CONV_UMMA: too many pixels");
+  MCVD_CHECK((long long)op.B * op.H * op.W < (1LL << 31) && a.Qtot < (1LL << 31), "CONV_UMMA: too many pixels");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  a.tiles_n = op.Cout / a.NT;
+  // accumulators per tile: i2 = 1|2 explicit, 0 = auto (2 when the double-buffered pair fits TMEM and the
+  // grid still fills the machine)
+  a.NACC = op.i2;
+  if (a.NACC == 0) {
+    a.NACC = (2 * 2 * a.NT <= 512) ? 2 : 1;
+    if (a.NACC == 2 && ((a.Qtot + 2 * MT - 1) / (2 * MT)) * a.tiles_n < sms) a.NACC = 1;
+  }
+  MCVD_CHECK(a.NACC == 1 || a.NACC == 2, "CONV_UMMA: accumulators %d", a.NACC);
+  a.nsets = (2 * a.NACC * a.NT <= 512) ? 2 : 1;
   const int MTOT = MT * a.NACC;
   a.halo0 = (a.ks == 3) ? a.Wp + 1 : 0;
   a.HP = (MTOT + 2 * a.halo0 + 7) & ~7;
+  MCVD_CHECK(a.HP <= 3 * NPROD, "CONV_UMMA: image width %d too large for the slab", op.W);
   a.nKB = (op.C0 + op.C1) / a.KB;
   a.act_in = (op.flags & MCVD_F_ACT_IN) ? 1 : 0;
   a.act_out = (op.flags & MCVD_F_ACT_OUT) ? 1 : 0;
   a.wscale = op.f1; a.oscale = op.f0;
-  int cols = a.NACC * a.NT, p2 = 32;
+  int cols = a.nsets * a.NACC * a.NT, p2 = 32;
   while (p2 < cols) p2 <<= 1;
   MCVD_CHECK(p2 <= 512, "CONV_UMMA: %d TMEM columns", cols);
   a.tmem_cols = p2;
-  const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
-  const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
   {
     int nb = a.HP / a.Pimg + 2;
     MCVD_CHECK(nb <= TAB_NB || !a.tab, "CONV_UMMA: %dx%d images are too small for the fused-norm path", op.H, op.W);
     a.tab_nb = (nb <= TAB_NB) ? nb : 0;
   }
-  const size_t tab_bytes = (size_t)2 * TAB_NB * 32 * 16 + 256 * 4;   // norm-table stage + bias
-  const size_t fixed = 2 * a_stage + (size_t)a.HP * 8 + 256 + tab_bytes;
+  const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
+  const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
+  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16;
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);
-  if (NB > 8) NB = 8;
+  if (NB > 10) NB = 10;
   a.NB = NB;
-  size_t ab = 2 * a_stage + (size_t)NB * b_stage;
-  if (ab < 32768) ab = 32768;
-  a.ab_bytes = (int)ab;
-  const size_t smem = ab + (size_t)a.HP * 8 + 256 + tab_bytes;
+  const size_t smem = fixed + (size_t)NB * b_stage;
   cudaError_t e = cudaFuncSetAttribute(k_conv_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit);
   MCVD_CHECK(e == cudaSuccess, "CONV_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  long long tiles = (a.Qtot + MTOT - 1) / MTOT;
-  dim3 grid((unsigned)tiles, (unsigned)(op.Cout / a.NT));
+  const long long tiles_m = (a.Qtot + MTOT - 1) / MTOT;
+  a.ntiles = (int)(tiles_m * a.tiles_n);
+  const int grid = a.ntiles < sms ? a.ntiles : sms;
   k_conv_umma<<<grid, NTHREADS, smem, s>>>(a);
   MCVD_CUDA_LAUNCH_CHECK("conv_umma");
   return 0;

@@ -232,11 +232,7 @@ class Engine:
                 if pk not in self.packed:
                     self.packed[pk] = self._pack_umma(taps, nt, kb)
                 wp, wscale = self.packed[pk]
-                pimg = (H + 1) * (H + 1) if ks == 3 else H * H
-                qtot = B * pimg
-                nacc = 2
-                if -(-qtot // 256) * (cout // nt) < 148 and -(-qtot // 128) > -(-qtot // 256):
-                    nacc = 1
+                nacc = 0                       # auto: chosen by the launcher (TMEM double-buffering, grid fill)
                 fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
                 emit(ops, lib.OP_CONV_UMMA, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=nt, i2=nacc,
                      f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, aux1=tab,

@@ -5,7 +5,7 @@ import torch
 from mcvd_b200 import lib
 from mcvd_b200.lib import McvdOp
 B, H, Cin, Cout = [int(v) for v in sys.argv[1:5]]; ks = int(sys.argv[5]) if len(sys.argv) > 5 else 3
-nacc = int(sys.argv[6]) if len(sys.argv) > 6 else 2
+nacc = int(sys.argv[6]) if len(sys.argv) > 6 else 0
 dev = "cuda:0"
 x = torch.randn(B, H, H, Cin, device=dev); w = torch.randn(ks * ks, Cin, Cout, device=dev) / math.sqrt(Cin * ks * ks)
 tab = torch.stack([torch.zeros(B, Cin), torch.ones(B, Cin), torch.ones(B, Cin), torch.zeros(B, Cin)], 2).contiguous().to(dev)
@@ -14,8 +14,6 @@ kb = lib.umma_kblock(Cin, 0); nt = max(d for d in range(16, 257, 16) if Cout % d
 pk = torch.empty(w.numel() * 4, dtype=torch.uint8, device=dev)
 lib.load().mcvd_umma_pack_weights(w.data_ptr(), ks * ks, Cin, Cout, nt, kb, pk.data_ptr(), 5, torch.cuda.current_stream().cuda_stream)
 pimg = (H + 1) * (H + 1) if ks == 3 else H * H
-tiles = -(-B * pimg // (128 * nacc)) * (Cout // nt)
-dbg = torch.zeros(tiles * 16, dtype=torch.int64, device=dev)
 o = McvdOp(); o.kind, o.B, o.H, o.W, o.C0, o.Cout, o.i0, o.i1, o.i2 = lib.OP_CONV_UMMA, B, H, H, Cin, Cout, ks, nt, nacc
 o.f0, o.f1 = 1.0, 2.0 ** -5; o.flags = lib.F_ACT_IN
 o.src0, o.w, o.bias, o.aux1, o.dst = x.data_ptr(), pk.data_ptr(), bias.data_ptr(), tab.data_ptr(), out.data_ptr()
@@ -25,12 +23,5 @@ torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); [lib.run_program(arr, 1, s) for _ in range(10)]; e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 100
-arr[0].dst2 = dbg.data_ptr(); lib.run_program(arr, 1, s); torch.cuda.synchronize()
-d = dbg.view(tiles, 16).double().mean(0).tolist()
 flops = 2.0 * B * H * H * Cin * Cout * ks * ks
-nkb = Cin // kb
-mma = nkb * ks * ks * (kb // 16) * nacc * 3 * nt / 2
-print(f"conv {Cin}->{Cout} k{ks} @{H}x{H} B={B} nt={nt} nacc={nacc} kb={kb}: {us:.1f} us/launch, {flops/us/1e6:.1f} TF/s algorithmic ({3*flops/us/1e6:.0f} executed), {tiles} CTAs")
-print(f" per CTA cycles: total {d[0]:.0f} | MMA-issue-done at {d[3]:.0f} (ideal tensor time {mma:.0f}) | MMA wait A_FULL {d[1]:.0f}, wait B_FULL {d[2]:.0f}")
-print(f"   epilogue items {d[11]:.0f}: tmem ld+wait {d[8]:.0f}, scale+STS+sync {d[9]:.0f}, shfl/LDS/STG {d[10]:.0f}")
-print(f"   producer(t0): wait A_EMPTY {d[4]:.0f}, produce {d[5]:.0f} ({d[5]/nkb:.0f}/K-block) | epilogue: wait ACC {d[6]:.0f}, drain {d[7]:.0f}")
+print(f"conv {Cin}->{Cout} k{ks} @{H}x{H} B={B} nt={nt} nacc={nacc} kb={kb}: {us:.1f} us/launch, {flops/us/1e6:.1f} TF/s algorithmic ({3*flops/us/1e6:.0f} executed)")
