@@ -53,6 +53,7 @@ struct UmmaArgs {
   const float* res;
   const float4* tab;     // norm table [B][Cin] (mean, rstd, G, S) or null
   float* dst;
+  long long* dbg;        // optional per-CTA cycle counters (tools/umma_timing.py); null in production
   int B, H, W, C0, C1, Cout;
   int ks;                // 1 or 3
   int Wp, Pimg;          // padded row pitch, positions per image
@@ -131,6 +132,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  const long long t_begin = dbg ? clock64() : 0;
+#define DBG_T(var) long long var = dbg ? clock64() : 0
+#define DBG_ADD(slot, since, cond) do { if (dbg && (cond)) { long long t__ = clock64(); dbg[slot] += t__ - since; since = t__; } } while (0)
 
   if (warp < 8) {
     // =========================== producers ===========================
@@ -145,16 +150,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       const long long q_first = (long long)(t / a.tiles_n) * MTOT - a.halo0;
       return q_first <= 0 ? 0 : (int)min((long long)(a.B - 1), q_first / a.Pimg);
     };
-    auto stage_table = [&](int tb0, int kb, int g) {       // table rows of K-block kb -> buffer g & 1
-      if (!has_tab) return;
-      float4* tsm = tab_s + (size_t)(g & 1) * TAB_NB * 32;
-      const int c0 = kb * a.KB;
-      for (int i = tid; i < a.tab_nb * a.KB; i += NPROD) {
-        const int bi = i / a.KB, c = i - bi * a.KB;
-        const int b = min(tb0 + bi, a.B - 1);
-        const float4 t = __ldg(a.tab + (long long)b * Cin + c0 + c);
-        tsm[bi * 32 + c] = make_float4(t.x, t.y * t.z, t.w, 0.f);
-      }
+    // norm-table rows of one K-block: <= TAB_NB * 32 = 256 float4, i.e. at most ONE per producer thread.
+    // Split into a register load (issued early, latency hidden behind the transform) and a smem store.
+    auto tab_load = [&](int tb0, int kb, float4& treg) {
+      if (!has_tab || tid >= a.tab_nb * a.KB) return;
+      const int bi = tid / a.KB, c = tid - bi * a.KB;
+      const int b = min(tb0 + bi, a.B - 1);
+      treg = __ldg(a.tab + (long long)b * Cin + kb * a.KB + c);
+    };
+    auto tab_store = [&](int g, const float4& treg) {           // -> buffer g & 1
+      if (!has_tab || tid >= a.tab_nb * a.KB) return;
+      const int bi = tid / a.KB, c = tid - bi * a.KB;
+      float* tb = reinterpret_cast<float*>(tab_s) + (size_t)(g & 1) * TAB_NB * 96 + bi * 96;   // [mean|rstd*G|S][32]
+      tb[c] = treg.x;
+      tb[32 + c] = treg.y * treg.z;
+      tb[64 + c] = treg.w;
     };
     auto emit = [&](const float4* raw, int pix, int bidx, int h, const float4* tsm, uint8_t* hi_base, uint8_t* lo_base) {
       if (pix == -2) return;
@@ -166,14 +176,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
             float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
                           raw[2 * ch + 1].x, raw[2 * ch + 1].y, raw[2 * ch + 1].z, raw[2 * ch + 1].w};
             if (has_tab) {
-              const float4* trow = tsm + bidx * 32 + ch * 8;
+              const float* tb = reinterpret_cast<const float*>(tsm) + bidx * 96 + ch * 8;
+              const float4 m0 = *reinterpret_cast<const float4*>(tb), m1 = *reinterpret_cast<const float4*>(tb + 4);
+              const float4 g0 = *reinterpret_cast<const float4*>(tb + 32), g1 = *reinterpret_cast<const float4*>(tb + 36);
+              const float4 s0 = *reinterpret_cast<const float4*>(tb + 64), s1 = *reinterpret_cast<const float4*>(tb + 68);
+              const float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+              const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float4 t = trow[e];                      // (mean, rstd*G, S, -)
-                float n = fmaf(v[e] - t.x, t.y, t.z);
-                if (a.act_in) n = silu_fast(n);
-                v[e] = n;
-              }
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e] - mm[e], gg[e], ss[e]);
+              if (a.act_in) silu_fast8(v);
             }
             uint32_t hw[4], lw[4];
 #pragma unroll
@@ -197,10 +209,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     };
 
     int g = 0;                                             // K-blocks produced so far (all tiles)
-    if ((int)blockIdx.x < a.ntiles) stage_table(tile_b0_of(blockIdx.x), 0, 0);
+    float4 treg = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((int)blockIdx.x < a.ntiles) { tab_load(tile_b0_of(blockIdx.x), 0, treg); tab_store(0, treg); }
+    const bool single = a.HP <= NPROD;                     // one slab row per thread: pipeline across K-blocks
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
       const long long p0 = (long long)(t / a.tiles_n) * MTOT;
       const int tb0 = tile_b0_of(t);
+      const bool more = t + (int)gridDim.x < a.ntiles;
+      const int tb_next = more ? tile_b0_of(t + gridDim.x) : 0;
       int ppix[3], pb[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -209,32 +225,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         pb[i] = 0;
         if (h < a.HP) { int b = tb0; ppix[i] = decode_pos(a, p0 - a.halo0 + h, b); pb[i] = b - tb0; }
       }
-      for (int kb = 0; kb < a.nKB; ++kb, ++g) {
-        const int st = g & 1;
+      auto src_of = [&](int kb, const float*& src, int& cs, int& cc0) {
         const int c0 = kb * a.KB;
-        const float* src;
-        int cs, cc0;
         if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
-        float4 raw0[8], raw1[8];
-        fetch(raw0, ppix[0], src, cs, cc0);              // requests in flight while we wait below
-        fetch(raw1, ppix[1], src, cs, cc0);
+      };
+      // one K-block: `cur` already holds (or receives) this K-block's channels of slab row 0; when `single`,
+      // the NEXT K-block's channels are requested into `nxt` before the transform starts.
+      auto step = [&](float4* cur, float4* nxt, int kb) {
+        const int st = g & 1;
+        const float* src; int cs, cc0;
+        src_of(kb, src, cs, cc0);
+        if (!single) { fetch(cur, ppix[0], src, cs, cc0); fetch(nxt, ppix[1], src, cs, cc0); }
+        else if (kb + 1 < a.nKB) { const float* s2; int cs2, cc2; src_of(kb + 1, s2, cs2, cc2); fetch(nxt, ppix[0], s2, cs2, cc2); }
+        if (kb + 1 < a.nKB) tab_load(tb0, kb + 1, treg); else if (more) tab_load(tb_next, 0, treg);
+        DBG_T(tp);
         mbar_wait(A_EMPTY(st), ((g >> 1) & 1) ^ 1);
+        DBG_ADD(1, tp, tid == 0);
         if (has_tab) asm volatile("bar.sync 1, 256;" ::: "memory");   // this K-block's table staged by all
+        DBG_ADD(2, tp, tid == 0);
         uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
         uint8_t* lo_base = hi_base + a_half_bytes;
-        const float4* tsm = tab_s + (size_t)st * TAB_NB * 32;
-        emit(raw0, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
-        emit(raw1, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
-        if (a.HP > 2 * NPROD) {                          // 128-wide images: a third slab row for some threads
-          fetch(raw0, ppix[2], src, cs, cc0);
-          emit(raw0, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
+        const float4* tsm = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tab_s) + (size_t)st * TAB_NB * 96);
+        emit(cur, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
+        if (!single) {
+          emit(nxt, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
+          if (a.HP > 2 * NPROD) {                        // 128-wide images: a third slab row for some threads
+            fetch(nxt, ppix[2], src, cs, cc0);
+            emit(nxt, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
+          }
         }
+        DBG_ADD(3, tp, tid == 0);
         fence_proxy_async();          // make the generic-proxy stores visible to the tensor-core proxy
         mbar_arrive(A_FULL(st));
+        DBG_ADD(4, tp, tid == 0);
         // table of the NEXT K-block (possibly of the next tile) into the other buffer; everyone finished
         // reading that buffer before passing this K-block's bar.sync
-        if (kb + 1 < a.nKB) stage_table(tb0, kb + 1, g + 1);
-        else if (t + (int)gridDim.x < a.ntiles) stage_table(tile_b0_of(t + gridDim.x), 0, g + 1);
+        if (kb + 1 < a.nKB || more) tab_store(g + 1, treg);
+        ++g;
+      };
+      float4 rawA[8], rawB[8];
+      if (single) { const float* s0; int cs0, cc0; src_of(0, s0, cs0, cc0); fetch(rawA, ppix[0], s0, cs0, cc0); }
+      for (int kb = 0; kb < a.nKB; kb += 2) {
+        step(rawA, rawB, kb);
+        if (kb + 1 < a.nKB) step(rawB, rawA, kb + 1);
       }
     }
   } else if (warp == W_LOAD) {
@@ -267,17 +300,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       int bst = 0, bph = 0, g = 0, it = 0;
       for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
         const int set = it % a.nsets;
+        DBG_T(tm);
         mbar_wait(ACC_EMPTY(set), ((it / a.nsets) & 1) ^ 1);      // epilogue drained this accumulator set
+        DBG_ADD(5, tm, true);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(set * a.NACC * a.NT);
         uint32_t accum = 0;                    // 0 only for the very first MMA of each accumulator
         for (int kb = 0; kb < a.nKB; ++kb, ++g) {
           const int st = g & 1;
+          DBG_ADD(8, tm, true);
           mbar_wait(A_FULL(st), (g >> 1) & 1);
+          DBG_ADD(6, tm, true);
           tc_fence_after();
           const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
           for (int tap = 0; tap < taps; ++tap) {
+            DBG_ADD(8, tm, true);
             mbar_wait(B_FULL(bst), bph);
+            DBG_ADD(7, tm, true);
             tc_fence_after();
             const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
             const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
@@ -305,6 +344,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
           umma_commit(A_EMPTY(st));           // slab of this K-block consumed
         }
         umma_commit(ACC_FULL(set));
+        DBG_ADD(8, tm, true);
       }
     }
     __syncwarp();
@@ -321,7 +361,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       const int set = it % a.nsets;
       const long long p0 = (long long)(t / a.tiles_n) * MTOT;
       const int n0 = (t % a.tiles_n) * a.NT;
+      DBG_T(te);
       mbar_wait(ACC_FULL(set), (it / a.nsets) & 1);
+      DBG_ADD(9, te, tid == W_EPI * 32);
       tc_fence_after();
       const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(set * a.NACC * a.NT);
       for (int acc = 0; acc < a.NACC; ++acc) {
@@ -370,10 +412,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       }
       tc_fence_before();
       mbar_arrive(ACC_EMPTY(set));            // 128 arrivals: this accumulator set may be overwritten
+      DBG_ADD(10, te, tid == W_EPI * 32);
     }
   }
 
   __syncthreads();
+  if (dbg && tid == 0) dbg[0] = clock64() - t_begin;
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
@@ -424,6 +468,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.wpk = (const __half*)op.w;
   a.bias = (const float*)op.bias; a.res = (const float*)op.aux0; a.tab = (const float4*)op.aux1;
   a.dst = (float*)op.dst;
+  a.dbg = (long long*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.Cout = op.Cout; a.ks = op.i0;
   a.NT = op.i1;
   a.KB = pick_kb(op.C0, op.C1);

@@ -157,17 +157,23 @@ __global__ void __launch_bounds__(128) k_gn_partial(const float* __restrict__ s0
     const float* ptr = src + ((long long)b * HW + p0) * cs + cc;
     double ds = 0.0, dq = 0.0;
     int p = p0;
-    while (p < p1) {
-      int pe = min(p + 32, p1);
+    // 8 independent loads in flight per lane; fp32 partials over 8 pixels, fp64 across groups
+    for (; p + 8 <= p1; p += 8) {
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __ldg(ptr + (long long)i * cs);
+      ptr += 8LL * cs;
       float fs = 0.f, fq = 0.f;
-      for (; p < pe; ++p) {
-        float v = *ptr;
-        ptr += cs;
-        fs += v;
-        fq = fmaf(v, v, fq);
-      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { fs += v[i]; fq = fmaf(v[i], v[i], fq); }
       ds += (double)fs;
       dq += (double)fq;
+    }
+    for (; p < p1; ++p) {
+      const float v = __ldg(ptr);
+      ptr += cs;
+      ds += (double)v;
+      dq += (double)v * (double)v;
     }
     part[((long long)b * nchunk + chunk) * C + c] = make_double2(ds, dq);
   }

@@ -119,6 +119,21 @@ __device__ __forceinline__ float silu_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
   return x * r;
 }
+// SiLU on 8 values with the five dependent stages issued stage-by-stage (8-way ILP; written out so the
+// compiler cannot fold the chains through one temporary when registers are tight)
+__device__ __forceinline__ void silu_fast8(float v[8]) {
+  float t[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) t[e] = v[e] * -1.4426950408889634f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(t[e]));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) t[e] += 1.0f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(t[e]));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] *= t[e];
+}
 // two fp32 -> fp16 hi pair + fp16 lo pair (lo = fp16(v - float(hi))); one packed convert per pair
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
