@@ -32,9 +32,11 @@ extern "C" {
 /* ---- op kinds ------------------------------------------------------------------------------- */
 enum {
   /* [B,C0,H,W] (+ [B,C1,H,W]) fp32 NCHW -> [B,H,W,C0+C1] NHWC.  torch.cat([x, cond], 1) +
-   * x.contiguous() of ncsnpp_more.py:256-257,293. */
+   * x.contiguous() of ncsnpp_more.py:256-257,293.  Cout > 0: destination channel pitch (extra channels
+   * are zero-filled so the first conv can run on the tensor cores with K a multiple of 16). */
   MCVD_OP_NCHW_TO_NHWC = 1,
-  /* [B,H,W,C0] NHWC -> [B,C0,H,W] NCHW (network output back to the reference layout). */
+  /* [B,H,W,C0] NHWC -> [B,C0,H,W] NCHW (network output back to the reference layout).  C1 > 0: source
+   * channel pitch (the last conv writes Cout padded to 16). */
   MCVD_OP_NHWC_TO_NCHW = 2,
   /* sinusoidal timestep embedding, layers.py:504-518.  src0 = t fp32 [B]; dst [B, Cout]. */
   MCVD_OP_TIMESTEP_EMBED = 3,
@@ -80,7 +82,7 @@ enum {
    * DDPM; :163-166 DDIM; denoise :331-333):
    *   x0 = f0 * (x - f1 * eps);  if MCVD_F_CLIP: x0 = clamp(x0,-1,1);
    *   x  = f2 * x0 + f3 * x + f4 * eps + f5 * z
-   * dst = x [B,C0,H,W] NCHW (in place); src0 = eps [B,H,W,C0] NHWC; src1 = z NCHW or NULL
+   * dst = x [B,C0,H,W] NCHW (in place); src0 = eps [B,H,W,C0] NHWC (channel pitch Cout if > 0); src1 = z NCHW or NULL
    * (MCVD_F_PHILOX: z from Philox4x32-10 keyed by (seed=i0|i1<<32, clip id = i2 + b, step = i3)). */
   MCVD_OP_DIFFUSION_UPDATE = 11,
   /* 3x3 / 1x1 convolution on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp16 hi/lo split of

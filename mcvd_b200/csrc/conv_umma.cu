@@ -487,8 +487,10 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   // grid still fills the machine)
   a.NACC = op.i2;
   if (a.NACC == 0) {
-    a.NACC = (2 * 2 * a.NT <= 512) ? 2 : 1;
-    if (a.NACC == 2 && ((a.Qtot + 2 * MT - 1) / (2 * MT)) * a.tiles_n < sms) a.NACC = 1;
+    // two accumulators (256-row tiles) halve the weight traffic per MAC and keep all 8 producer warps busy on
+    // 1x1 convs; fall back to 128-row tiles when that would leave SMs idle
+    a.NACC = (2 * a.NT <= 512) ? 2 : 1;
+    if (a.NACC == 2 && ((a.Qtot + 2 * MT - 1) / (2 * MT)) * a.tiles_n < (long long)sms * 9 / 10) a.NACC = 1;
   }
   MCVD_CHECK(a.NACC == 1 || a.NACC == 2, "CONV_UMMA: accumulators %d", a.NACC);
   a.nsets = (2 * a.NACC * a.NT <= 512) ? 2 : 1;

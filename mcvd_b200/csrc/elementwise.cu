@@ -9,30 +9,33 @@ namespace mcvd {
 // NCHW (+NCHW) -> NHWC  /  NHWC -> NCHW
 // ------------------------------------------------------------------------------------------------
 __global__ void k_nchw_to_nhwc(const float* __restrict__ s0, const float* __restrict__ s1, float* __restrict__ dst,
-                               int B, int HW, int C0, int C1) {
+                               int B, int HW, int C0, int C1, int pitch) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * HW) return;
   int b = (int)(i / HW), p = (int)(i % HW);
   int C = C0 + C1;
-  float* d = dst + i * C;
+  float* d = dst + i * pitch;
   for (int c = 0; c < C0; ++c) d[c] = s0[((long long)b * C0 + c) * HW + p];
   for (int c = 0; c < C1; ++c) d[C0 + c] = s1[((long long)b * C1 + c) * HW + p];
+  for (int c = C; c < pitch; ++c) d[c] = 0.f;          // zero channel padding (tensor-core K alignment)
 }
 
 int launch_nchw_to_nhwc(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.dst && (op.C1 == 0 || op.src1), "NCHW_TO_NHWC: null pointer");
   long long n = (long long)op.B * op.H * op.W;
   k_nchw_to_nhwc<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)op.src0, (const float*)op.src1,
-                                                             (float*)op.dst, op.B, op.H * op.W, op.C0, op.C1);
+                                                             (float*)op.dst, op.B, op.H * op.W, op.C0, op.C1,
+                                                             op.Cout > 0 ? op.Cout : op.C0 + op.C1);
   MCVD_CUDA_LAUNCH_CHECK("nchw_to_nhwc");
   return 0;
 }
 
-__global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int B, int HW, int C) {
+__global__ void k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int B, int HW, int C,
+                               int pitch) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * HW) return;
   int b = (int)(i / HW), p = (int)(i % HW);
-  const float* sp = src + i * C;
+  const float* sp = src + i * pitch;
   for (int c = 0; c < C; ++c) dst[((long long)b * C + c) * HW + p] = sp[c];
 }
 
@@ -40,7 +43,7 @@ int launch_nhwc_to_nchw(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.dst, "NHWC_TO_NCHW: null pointer");
   long long n = (long long)op.B * op.H * op.W;
   k_nhwc_to_nchw<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)op.src0, (float*)op.dst, op.B,
-                                                             op.H * op.W, op.C0);
+                                                             op.H * op.W, op.C0, op.C1 > 0 ? op.C1 : op.C0);
   MCVD_CUDA_LAUNCH_CHECK("nhwc_to_nchw");
   return 0;
 }
@@ -435,7 +438,7 @@ __device__ __forceinline__ float philox_normal(uint32_t seed_lo, uint32_t seed_h
 }
 
 __global__ void k_diffusion_update(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z,
-                                   int B, int C, int HW, float k0, float k1, float ca, float cb, float cc,
+                                   int B, int C, int HW, int pitch, float k0, float k1, float ca, float cb, float cc,
                                    float sigma, int flags, uint32_t seed_lo, uint32_t seed_hi, int clip0, int step) {
   long long total = (long long)B * C * HW;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -444,7 +447,7 @@ __global__ void k_diffusion_update(float* __restrict__ x, const float* __restric
   int c = (int)((i / HW) % C);
   int b = (int)(i / ((long long)HW * C));
   float xv = x[i];
-  float ev = eps[((long long)b * HW + p) * C + c];
+  float ev = eps[((long long)b * HW + p) * pitch + c];
   float x0 = k0 * (xv - k1 * ev);
   if (flags & MCVD_F_CLIP) x0 = fminf(fmaxf(x0, -1.f), 1.f);
   float r = ca * x0 + cb * xv;
@@ -463,7 +466,8 @@ int launch_diffusion_update(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.f5 == 0.f || (op.flags & MCVD_F_PHILOX) || op.src1, "DIFFUSION_UPDATE: sigma != 0 needs noise");
   long long total = (long long)op.B * op.C0 * op.H * op.W;
   k_diffusion_update<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-      (float*)op.dst, (const float*)op.src0, (const float*)op.src1, op.B, op.C0, op.H * op.W, op.f0, op.f1, op.f2,
+      (float*)op.dst, (const float*)op.src0, (const float*)op.src1, op.B, op.C0, op.H * op.W,
+      op.Cout > 0 ? op.Cout : op.C0, op.f0, op.f1, op.f2,
       op.f3, op.f4, op.f5, op.flags, (uint32_t)op.i0, (uint32_t)op.i1, op.i2, op.i3);
   MCVD_CUDA_LAUNCH_CHECK("diffusion_update");
   return 0;

@@ -302,17 +302,21 @@ class Engine:
         P.cond_in = f32(B, ns.cond_ch, S, S) if ns.cond_ch > 0 else None
         P.t = f32(B)
         P.out = f32(B, ns.out_ch, S, S)
-        P.eps_nhwc = f32(B, S, S, ns.out_ch)
+        # skinny first / last convs: zero-pad K (input channels) / N (output channels) to 16 so they run on the
+        # tensor-core kernel instead of the CUDA-core ones
+        tc_edges = self.conv_mode == "umma"
+        in_pad = (ns.in_ch + 15) // 16 * 16 if tc_edges else ns.in_ch
+        out_pad = (ns.out_ch + 15) // 16 * 16 if tc_edges else ns.out_ch
         P.noise = f32(B, ns.out_ch, S, S)
         if ns.spade:
             P.cond_nhwc = f32(B, S, S, ns.cond_ch)
             emit(cnd, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.cond_ch, src0=P.cond_in, dst=P.cond_nhwc)
-            xin = f32(B, S, S, ns.in_ch)
-            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, src0=P.x_in, dst=xin)
+            xin = f32(B, S, S, in_pad)
+            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, Cout=in_pad, src0=P.x_in, dst=xin)
         else:
-            xin = f32(B, S, S, ns.in_ch)
-            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, C1=ns.cond_ch, src0=P.x_in, src1=P.cond_in,
-                 dst=xin)
+            xin = f32(B, S, S, in_pad)
+            emit(step, lib.OP_NCHW_TO_NHWC, H=S, W=S, C0=ns.out_ch, C1=ns.cond_ch, Cout=in_pad, src0=P.x_in,
+                 src1=P.cond_in, dst=xin)
 
         # ---- time embedding + all FiLM projections (ncsnpp_more.py:273-280; layerspp.py:521) --------
         mods = ns.mods
@@ -388,7 +392,13 @@ class Engine:
             return conv(step, pre + "NIN_3", Src(att, C), H, C, 1, pre + "NIN_3.W", pre + "NIN_3.b", residual=x,
                         scale=INV_SQRT2, nin=True)
 
-        h = conv(step, "first", Src(xin, ns.in_ch), S, ns.nf, 3, "unet.all_modules.2.weight", "unet.all_modules.2.bias")
+        w_first = self._conv_taps(sd("unet.all_modules.2.weight"))
+        if in_pad != ns.in_ch:
+            wp_ = torch.zeros(9, in_pad, ns.nf, device=dev, dtype=torch.float32)
+            wp_[:, :ns.in_ch] = w_first
+            w_first = wp_
+        h = conv(step, "first", Src(xin, in_pad), S, ns.nf, 3, None, None, wcat=w_first,
+                 bcat=sd("unet.all_modules.2.bias").float().contiguous())
         hs: List[Tuple[torch.Tensor, int]] = [(h, ns.nf)]
         cur, cur_c = h, ns.nf
         for ms in mods[3:-2]:
@@ -429,10 +439,19 @@ class Engine:
             tabn = norm_table(step, Src(cur, cur_c), S, 1e-5,
                               affine=(sd(pre + "Norm_0.weight"), sd(pre + "Norm_0.bias")))
             last_src = cur
-        if ns.out_ch <= 16 and coutp * 9 * cur_c * 4 <= 200 * 1024:
+        if tc_edges:
+            wl_p = torch.zeros(9, cur_c, out_pad, device=dev, dtype=torch.float32)
+            wl_p[:, :, :ns.out_ch] = wl
+            bl_p = torch.zeros(out_pad, device=dev, dtype=torch.float32)
+            bl_p[:ns.out_ch] = bl
+            P.eps_nhwc = conv(step, "last", Src(last_src, cur_c), S, out_pad, 3, None, None, tab=tabn, act_in=True,
+                              wcat=wl_p, bcat=bl_p)
+        elif ns.out_ch <= 16 and coutp * 9 * cur_c * 4 <= 200 * 1024:
+            P.eps_nhwc = f32(B, S, S, ns.out_ch)
             emit(step, lib.OP_CONV_SMALLN, H=S, W=S, C0=cur_c, Cout=ns.out_ch, i1=coutp, src0=last_src, w=wlp, bias=bl,
                  aux0=tabn, dst=P.eps_nhwc, flags=lib.F_ACT_OUT)
         else:
+            P.eps_nhwc = f32(B, S, S, ns.out_ch)
             if tabn is not None:
                 an = f32(B, S, S, cur_c)
                 emit(step, lib.OP_APPLY, H=S, W=S, C0=cur_c, src0=cur, aux0=tabn, dst=an, flags=lib.F_ACT_OUT)
@@ -446,11 +465,13 @@ class Engine:
         # eps NHWC -> NCHW for the module-level forward()
         o = McvdOp()
         o.kind, o.B, o.H, o.W, o.C0 = lib.OP_NHWC_TO_NCHW, B, S, S, ns.out_ch
+        o.C1 = out_pad
         o.src0, o.dst = P.eps_nhwc.data_ptr(), P.out.data_ptr()
         P.out_arr = lib.make_ops([o])
         # reverse-diffusion update (coefficients patched per step by the sampler)
         u = McvdOp()
         u.kind, u.B, u.H, u.W, u.C0 = lib.OP_DIFFUSION_UPDATE, B, S, S, ns.out_ch
+        u.Cout = out_pad
         u.src0, u.src1, u.dst = P.eps_nhwc.data_ptr(), P.noise.data_ptr(), P.x_in.data_ptr()
         P.update_arr = lib.make_ops([u])
         lib.validate_program(P.step_arr, len(step))

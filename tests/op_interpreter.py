@@ -85,9 +85,14 @@ class Interpreter:
             a = self.get(op.src0, B * op.C0 * H * W).view(B, op.C0, H, W)
             if op.C1 > 0:
                 a = torch.cat([a, self.get(op.src1, B * op.C1 * H * W).view(B, op.C1, H, W)], 1)
-            self.get(op.dst, a.numel()).copy_(a.permute(0, 2, 3, 1).reshape(-1))
+            a = a.permute(0, 2, 3, 1)
+            pitch = op.Cout if op.Cout > 0 else a.shape[3]
+            if pitch > a.shape[3]:
+                a = F.pad(a, (0, pitch - a.shape[3]))
+            self.get(op.dst, a.numel()).copy_(a.reshape(-1))
         elif k == lib.OP_NHWC_TO_NCHW:
-            a = self.get(op.src0, B * H * W * op.C0).view(B, H, W, op.C0)
+            pitch = op.C1 if op.C1 > 0 else op.C0
+            a = self.get(op.src0, B * H * W * pitch).view(B, H, W, pitch)[..., :op.C0]
             self.get(op.dst, a.numel()).copy_(a.permute(0, 3, 1, 2).reshape(-1))
         elif k == lib.OP_TIMESTEP_EMBED:
             dim = op.Cout
@@ -226,7 +231,8 @@ class Interpreter:
         elif k == lib.OP_DIFFUSION_UPDATE:
             C = op.C0
             x = self.get(op.dst, B * C * H * W).view(B, C, H, W)
-            eps = self.get(op.src0, B * H * W * C).view(B, H, W, C).permute(0, 3, 1, 2)
+            pitch = op.Cout if op.Cout > 0 else C
+            eps = self.get(op.src0, B * H * W * pitch).view(B, H, W, pitch)[..., :C].permute(0, 3, 1, 2)
             x0 = op.f0 * (x - op.f1 * eps)
             if op.flags & lib.F_CLIP:
                 x0 = x0.clamp(-1, 1)
