@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   auto B_EMPTY = [&](int i) { return bar0 + 8u * (8 + a.NB + i); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   float4* tab_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][TAB_NB][32]
+  float* bias_s = reinterpret_cast<float*>(tab_s + 2 * TAB_NB * 32);                    // [NT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = a.ks * a.ks;
@@ -354,13 +355,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     // block is transposed through an XOR-swizzled 4 KB shared-memory pad so that every global load / store
     // instruction covers whole 128-byte lines of `dst` / `res` (8 lanes per row).
     const int lq = warp & 3;
+    const int et = tid - W_EPI * 32;                           // 0..127 within the epilogue group
     float4* pad = pads + (size_t)(warp - W_EPI) * 256;        // [32 rows][8 float4]
     const int nblk = (a.NT + 31) / 32;
+    const float* __restrict__ resp = a.res;
+    float* __restrict__ dstp = a.dst;
     int it = 0;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++it) {
       const int set = it % a.nsets;
       const long long p0 = (long long)(t / a.tiles_n) * MTOT;
       const int n0 = (t % a.tiles_n) * a.NT;
+      // bias of this n-tile -> smem (read back as broadcast float4s); guarded by the group's named barrier
+      asm volatile("bar.sync 2, 128;" ::: "memory");           // previous tile's readers are done
+      for (int i = et; i < a.NT; i += 128) bias_s[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
       DBG_T(te);
       mbar_wait(ACC_FULL(set), (it / a.nsets) & 1);
       DBG_ADD(9, te, tid == W_EPI * 32);
@@ -369,6 +377,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       for (int acc = 0; acc < a.NACC; ++acc) {
         int bdummy = 0;
         const int mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bdummy);
+        // row slots of this lane in the transposed (coalesced) phase, for 32-wide blocks: 8 lanes per row
+        int px8[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) px8[k] = __shfl_sync(0xffffffffu, mypix, k * 4 + (lane >> 3));
+        const int q8 = lane & 7;
+        float4 rnext[8];
+        auto res_fetch = [&](int blk) {                       // residual of a full 32-wide block -> registers
+          if (!resp) return;
+          const int cb = blk * 32;
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (px8[k] >= 0) rnext[k] = __ldg(reinterpret_cast<const float4*>(resp + (long long)px8[k] * a.Cout + n0 + cb + q8 * 4));
+        };
+        if (a.NT >= 32) res_fetch(0);
         for (int blk = 0; blk < nblk; ++blk) {
           const int cb = blk * 32;
           const int w = min(32, a.NT - cb);                 // 32 or 16 columns
@@ -383,27 +405,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
                   make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
                               __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
           __syncwarp();
-          const int lpr = w >> 2;                           // lanes per row (8 or 4)
-          const int rpi = 32 / lpr;                         // rows per instruction (4 or 8)
-          const int q = lane % lpr, rsub = lane / lpr;
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + cb + q * 4));
+          if (w == 32) {
+            float4 rcur[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k * rpi < 32) {
-              const int row = k * rpi + rsub;
+            for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
+            if ((blk + 1) * 32 + 32 <= a.NT) res_fetch(blk + 1);      // next full block's residual in flight
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q8 * 4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int row = k * 4 + (lane >> 3);
+              if (px8[k] >= 0) {
+                float4 v = pad[row * 8 + (q8 ^ (row & 7))];
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                if (resp) { v.x += rcur[k].x; v.y += rcur[k].y; v.z += rcur[k].z; v.w += rcur[k].w; }
+                v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
+                if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+                *reinterpret_cast<float4*>(dstp + (long long)px8[k] * a.Cout + n0 + cb + q8 * 4) = v;
+              }
+            }
+          } else {                                          // 16-wide tail: 4 lanes per row, 8 rows per instruction
+            const int q = lane & 3, rsub = lane >> 2;
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int row = k * 8 + rsub;
               const int px = __shfl_sync(0xffffffffu, mypix, row);
               if (px >= 0) {
                 float4 v = pad[row * 8 + (q ^ (row & 7))];
                 v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                 const long long off = (long long)px * a.Cout + n0 + cb + q * 4;
-                if (a.res) {
-                  const float4 rv = __ldg(reinterpret_cast<const float4*>(a.res + off));
+                if (resp) {
+                  const float4 rv = __ldg(reinterpret_cast<const float4*>(resp + off));
                   v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
                 }
                 v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
                 if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-                *reinterpret_cast<float4*>(a.dst + off) = v;
+                *reinterpret_cast<float4*>(dstp + off) = v;
               }
             }
           }
@@ -489,7 +526,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   if (a.NACC == 0) {
     // two accumulators (256-row tiles) halve the weight traffic per MAC and keep all 8 producer warps busy on
     // 1x1 convs; fall back to 128-row tiles when that would leave SMs idle
-    a.NACC = (2 * a.NT <= 512) ? 2 : 1;
+    a.NACC = (2 * 2 * a.NT <= 512) ? 2 : 1;      // only when the double-buffered pair still fits TMEM (measured)
     if (a.NACC == 2 && ((a.Qtot + 2 * MT - 1) / (2 * MT)) * a.tiles_n < (long long)sms * 9 / 10) a.NACC = 1;
   }
   MCVD_CHECK(a.NACC == 1 || a.NACC == 2, "CONV_UMMA: accumulators %d", a.NACC);
@@ -513,7 +550,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   }
   const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
   const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
-  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16;
+  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16 + 1024;   // ... + bias
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);

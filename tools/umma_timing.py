@@ -6,6 +6,7 @@ from mcvd_b200 import lib
 from mcvd_b200.lib import McvdOp
 B, H, Cin, Cout = [int(v) for v in sys.argv[1:5]]; ks = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 nacc = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+mode = sys.argv[7] if len(sys.argv) > 7 else "tab"   # tab | plain | res
 dev = "cuda:0"
 x = torch.randn(B, H, H, Cin, device=dev); w = torch.randn(ks * ks, Cin, Cout, device=dev) / math.sqrt(Cin * ks * ks)
 tab = torch.stack([torch.zeros(B, Cin), torch.ones(B, Cin), torch.ones(B, Cin), torch.zeros(B, Cin)], 2).contiguous().to(dev)
@@ -15,8 +16,11 @@ pk = torch.empty(w.numel() * 4, dtype=torch.uint8, device=dev)
 lib.load().mcvd_umma_pack_weights(w.data_ptr(), ks * ks, Cin, Cout, nt, kb, pk.data_ptr(), 5, torch.cuda.current_stream().cuda_stream)
 pimg = (H + 1) * (H + 1) if ks == 3 else H * H
 o = McvdOp(); o.kind, o.B, o.H, o.W, o.C0, o.Cout, o.i0, o.i1, o.i2 = lib.OP_CONV_UMMA, B, H, H, Cin, Cout, ks, nt, nacc
-o.f0, o.f1 = 1.0, 2.0 ** -5; o.flags = lib.F_ACT_IN
-o.src0, o.w, o.bias, o.aux1, o.dst = x.data_ptr(), pk.data_ptr(), bias.data_ptr(), tab.data_ptr(), out.data_ptr()
+o.f0, o.f1 = 1.0, 2.0 ** -5
+o.src0, o.w, o.bias, o.dst = x.data_ptr(), pk.data_ptr(), bias.data_ptr(), out.data_ptr()
+res = torch.randn(B, H, H, Cout, device=dev)
+if mode == "tab": o.aux1 = tab.data_ptr(); o.flags = lib.F_ACT_IN
+if mode == "res": o.aux0 = res.data_ptr()
 arr = lib.make_ops([o]); s = torch.cuda.current_stream().cuda_stream
 for _ in range(3): lib.run_program(arr, 1, s)
 torch.cuda.synchronize()
