@@ -56,14 +56,18 @@ enum {
    *                               (scale/shift = chunk(Dense_0(act(temb)), 2), layerspp.py:521-523,536)
    *   aux0 != NULL, !FILM       : G = aux0[c] (GroupNorm weight), S = aux1[c] (bias)
    *   aux0 == NULL              : G = 1, S = 0
-   * src0 = partials, i0 = chunks, C0 = total channels, f0 = eps, f1 = 1/(pixels * i1). */
+   * src0 = per-channel partials of the first tensor ([B,i0,C0]); src1/C1 = partials of a second tensor
+   * (virtual concat) or NULL/0; i0 = chunks, f0 = eps.  Partials are per TENSOR, so a tensor consumed by
+   * several norms (skip connections) is scanned once. */
   MCVD_OP_GN_FINALIZE = 6,
   /* normalise + FiLM (+ SPADE gamma/beta) + SiLU + optional 4x4 FIR up/down-sampling, fp32 NHWC in
    * and out.  get_act_norm.forward layerspp.py:518-549, MySPADE.forward :152-173 (norm part),
    * upsample_2d / downsample_2d up_or_down_sampling.py:196-258 == upfirdn2d.  H,W are OUTPUT
    * dims; src0/src1 are the (virtually concatenated) inputs at input resolution; aux0 = float4
    * table from GN_FINALIZE (NULL = raw pass-through, used for the skip branch FIR(x));
-   * aux1/aux2 = SPADE gamma/beta [B,Hin,Win,C] or NULL. */
+   * aux1/aux2 = SPADE gamma/beta [B,Hin,Win,C] or NULL.  dst2 != NULL additionally receives the same
+   * resampling of the RAW input (the skip branch FIR(x) of up/down blocks, layerspp.py:600-611) so the
+   * input is read once. */
   MCVD_OP_APPLY = 7,
   /* direct convolution as implicit GEMM on CUDA cores (fp32 FFMA), NHWC.  nn.Conv2d 3x3 pad 1 /
    * 1x1 (layers.py:89-113) and NIN (layers.py:541-544).  i0 = ksize (1|3); src0/src1 virtual

@@ -196,16 +196,20 @@ int launch_gn_partial(const McvdOp& op, cudaStream_t s) {
 }
 
 // Pass 2: grid (groups, B); reduce partials, emit (mean, rstd, G, S) per channel.
-__global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__ part, float4* __restrict__ tab,
+__global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__ part0,
+                                                     const double2* __restrict__ part1, float4* __restrict__ tab,
                                                      const float* __restrict__ aux0, const float* __restrict__ aux1,
-                                                     int C, int cg, int nchunk, int HW, float eps, int film,
+                                                     int C0, int C1, int cg, int nchunk, int HW, float eps, int film,
                                                      int film_stride, int film_off) {
   int g = blockIdx.x, b = blockIdx.y;
+  const int C = C0 + C1;
   int n = nchunk * cg;
   double ds = 0.0, dq = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int chunk = i / cg, ci = i % cg;
-    double2 v = part[((long long)b * nchunk + chunk) * C + g * cg + ci];
+    int chunk = i / cg, c = g * cg + i % cg;
+    // per-channel partials live with the tensor that owns the channel (virtual concat of two tensors)
+    double2 v = (c < C0) ? part0[((long long)b * nchunk + chunk) * C0 + c]
+                         : part1[((long long)b * nchunk + chunk) * C1 + (c - C0)];
     ds += v.x;
     dq += v.y;
   }
@@ -244,13 +248,15 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__
 
 int launch_gn_finalize(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.dst, "GN_FINALIZE: null pointer");
-  int C = op.C0, cg = op.i1;
+  int C = op.C0 + op.C1, cg = op.i1;
   MCVD_CHECK(cg > 0 && C % cg == 0, "GN_FINALIZE: channels %d not divisible by group size %d", C, cg);
+  MCVD_CHECK(op.C1 == 0 || op.src1, "GN_FINALIZE: second partial array missing");
   int film = (op.flags & MCVD_F_FILM) ? 1 : 0;
   MCVD_CHECK(!op.aux0 || film || op.aux1, "GN_FINALIZE: affine needs weight and bias");
   dim3 grid(C / cg, op.B);
-  k_gn_finalize<<<grid, 128, 0, s>>>((const double2*)op.src0, (float4*)op.dst, (const float*)op.aux0,
-                                     (const float*)op.aux1, C, cg, op.i0, op.H * op.W, op.f0, film, op.i2, op.i3);
+  k_gn_finalize<<<grid, 128, 0, s>>>((const double2*)op.src0, (const double2*)op.src1, (float4*)op.dst,
+                                     (const float*)op.aux0, (const float*)op.aux1, op.C0, op.C1, cg, op.i0,
+                                     op.H * op.W, op.f0, film, op.i2, op.i3);
   MCVD_CUDA_LAUNCH_CHECK("gn_finalize");
   return 0;
 }
@@ -267,16 +273,20 @@ struct ApplyArgs {
   const float* gam;
   const float* bet;
   float* dst;
+  float* dst2;      // optional: the same resampling applied to the RAW input (skip branch of up/down blocks)
   int B, H, W, Hin, Win, C0, C1, flags;
 };
 
-__device__ __forceinline__ float4 apply_fetch(const ApplyArgs& a, int b, int yi, int xi, int c, const float4 t[4]) {
-  // value of the transformed input at input pixel (yi, xi), channels c..c+3 (zero outside)
-  if (yi < 0 || yi >= a.Hin || xi < 0 || xi >= a.Win) return make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ float4 apply_fetch(const ApplyArgs& a, int b, int yi, int xi, int c, const float4 t[4],
+                                              float4& raw) {
+  // value of the transformed input at input pixel (yi, xi), channels c..c+3 (zero outside); raw = untransformed
+  raw = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (yi < 0 || yi >= a.Hin || xi < 0 || xi >= a.Win) return raw;
   long long pix = ((long long)b * a.Hin + yi) * a.Win + xi;
   float4 v;
   if (c < a.C0) v = *reinterpret_cast<const float4*>(a.s0 + pix * a.C0 + c);
   else v = *reinterpret_cast<const float4*>(a.s1 + pix * a.C1 + (c - a.C0));
+  raw = v;
   if (a.tab) {
     float r[4] = {v.x, v.y, v.z, v.w};
     float gm[4] = {0.f, 0.f, 0.f, 0.f}, bt[4] = {0.f, 0.f, 0.f, 0.f};
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) t[k] = a.tab[(long long)b * C + c + k];
     }
-    float4 out;
+    float4 out, out2 = make_float4(0.f, 0.f, 0.f, 0.f), rw;
     if (a.flags & MCVD_F_DOWN) {
       // out[y,x] = sum_{i,j} k[i]k[j]/64 * in[2y+i-1, 2x+j-1]
       const float kw[4] = {1.f, 3.f, 3.f, 1.f};
@@ -332,8 +342,9 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-          float4 v = apply_fetch(a, b, 2 * y + ii - 1, 2 * x + jj - 1, c, t);
+          float4 v = apply_fetch(a, b, 2 * y + ii - 1, 2 * x + jj - 1, c, t, rw);
           fma4(out, kw[ii] * kw[jj] * (1.f / 64.f), v);
+          fma4(out2, kw[ii] * kw[jj] * (1.f / 64.f), rw);
         }
     } else if (a.flags & MCVD_F_UP) {
       // even y=2a: (in[a-1] + 3 in[a]) / 4 ; odd y=2a+1: (3 in[a] + in[a+1]) / 4   (per axis)
@@ -343,13 +354,16 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
       if (y & 1) { y0 = ya; y1 = ya + 1; wy0 = 3.f; wy1 = 1.f; } else { y0 = ya - 1; y1 = ya; wy0 = 1.f; wy1 = 3.f; }
       if (x & 1) { x0 = xa; x1 = xa + 1; wx0 = 3.f; wx1 = 1.f; } else { x0 = xa - 1; x1 = xa; wx0 = 1.f; wx1 = 3.f; }
       out = make_float4(0.f, 0.f, 0.f, 0.f);
-      fma4(out, wy0 * wx0 * (1.f / 16.f), apply_fetch(a, b, y0, x0, c, t));
-      fma4(out, wy0 * wx1 * (1.f / 16.f), apply_fetch(a, b, y0, x1, c, t));
-      fma4(out, wy1 * wx0 * (1.f / 16.f), apply_fetch(a, b, y1, x0, c, t));
-      fma4(out, wy1 * wx1 * (1.f / 16.f), apply_fetch(a, b, y1, x1, c, t));
+      float4 v;
+      v = apply_fetch(a, b, y0, x0, c, t, rw); fma4(out, wy0 * wx0 * (1.f / 16.f), v); fma4(out2, wy0 * wx0 * (1.f / 16.f), rw);
+      v = apply_fetch(a, b, y0, x1, c, t, rw); fma4(out, wy0 * wx1 * (1.f / 16.f), v); fma4(out2, wy0 * wx1 * (1.f / 16.f), rw);
+      v = apply_fetch(a, b, y1, x0, c, t, rw); fma4(out, wy1 * wx0 * (1.f / 16.f), v); fma4(out2, wy1 * wx0 * (1.f / 16.f), rw);
+      v = apply_fetch(a, b, y1, x1, c, t, rw); fma4(out, wy1 * wx1 * (1.f / 16.f), v); fma4(out2, wy1 * wx1 * (1.f / 16.f), rw);
     } else {
-      out = apply_fetch(a, b, y, x, c, t);
+      out = apply_fetch(a, b, y, x, c, t, rw);
+      out2 = rw;
     }
+    if (a.dst2) *reinterpret_cast<float4*>(a.dst2 + pix * C + c) = out2;
     *reinterpret_cast<float4*>(a.dst + pix * C + c) = out;
   }
 }
@@ -360,7 +374,7 @@ int launch_apply(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(!(op.aux1) || (op.aux2 && op.aux0), "APPLY: SPADE needs gamma, beta and the norm table");
   ApplyArgs a;
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.tab = (const float4*)op.aux0;
-  a.gam = (const float*)op.aux1; a.bet = (const float*)op.aux2; a.dst = (float*)op.dst;
+  a.gam = (const float*)op.aux1; a.bet = (const float*)op.aux2; a.dst = (float*)op.dst; a.dst2 = (float*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.flags = op.flags;
   a.Hin = op.H; a.Win = op.W;
   if (op.flags & MCVD_F_DOWN) { a.Hin = op.H * 2; a.Win = op.W * 2; }

@@ -255,16 +255,26 @@ class Engine:
             return dst
 
         # ---- GroupNorm statistics -> (mean, rstd, G, S) table -----------------------------------
+        part_cache: Dict[int, torch.Tensor] = {}
+
+        def partials_of(ops, t: torch.Tensor, C: int, H: int, nchunk: int):
+            """per-channel (sum, sum of squares) of one tensor, computed ONCE however many norms read it"""
+            key = t.data_ptr()
+            if key not in part_cache:
+                part = torch.empty(B * nchunk * C * 2, device=dev, dtype=torch.float64)
+                keep(part)
+                emit(ops, lib.OP_GN_PARTIAL, H=H, W=H, C0=C, i0=nchunk, src0=t, dst=part)
+                part_cache[key] = part
+            return part_cache[key]
+
         def norm_table(ops, src: Src, H: int, eps: float, film_off=None, affine=None):
             C = src.C
             cg = C // arch.num_groups(C)
             nchunk = max(1, (H * H) // GN_PPC)
-            part = torch.empty(B * nchunk * C * 2, device=dev, dtype=torch.float64)
-            keep(part)
             tab = f32(B, C, 4)
-            emit(ops, lib.OP_GN_PARTIAL, H=H, W=H, C0=src.c0, C1=src.c1, i0=nchunk, src0=src.t0, src1=src.t1,
-                 dst=part)
-            kw = dict(H=H, W=H, C0=C, i0=nchunk, i1=cg, f0=eps, src0=part, dst=tab)
+            p0 = partials_of(ops, src.t0, src.c0, H, nchunk)
+            p1 = partials_of(ops, src.t1, src.c1, H, nchunk) if src.t1 is not None else None
+            kw = dict(H=H, W=H, C0=src.c0, C1=src.c1, i0=nchunk, i1=cg, f0=eps, src0=p0, src1=p1, dst=tab)
             if film_off is not None:
                 kw.update(aux0=P.film, i2=ns.film_total, i3=film_off, flags=lib.F_FILM)
                 if ops is step:
@@ -347,12 +357,10 @@ class Engine:
                 if ns.spade:
                     g0, b0 = spade_gb(pre + "actnorm0.Norm_0.", Cin, Hin)
                 a0 = f32(B, H, H, Cin)
+                xs = f32(B, H, H, Cin) if resample else None   # FIR of the skip branch too (layerspp.py:600-611)
                 emit(step, lib.OP_APPLY, H=H, W=H, C0=src.c0, C1=src.c1, src0=src.t0, src1=src.t1, aux0=tab0, aux1=g0,
-                     aux2=b0, dst=a0, flags=lib.F_ACT_OUT | resample)
-                if resample:                          # FIR applied to the skip branch too (layerspp.py:600-611)
-                    xs = f32(B, H, H, Cin)
-                    emit(step, lib.OP_APPLY, H=H, W=H, C0=src.c0, C1=src.c1, src0=src.t0, src1=src.t1, dst=xs,
-                         flags=resample)
+                     aux2=b0, dst=a0, dst2=xs, flags=lib.F_ACT_OUT | resample)
+                if resample:
                     sc_src = Src(xs, Cin)
                 h = conv(step, pre + "Conv_0", Src(a0, Cin), H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias")
             else:

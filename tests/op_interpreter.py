@@ -77,6 +77,20 @@ class Interpreter:
         y = F.conv2d(x.permute(0, 3, 1, 2), wt, None, padding=ks // 2)
         return y.permute(0, 2, 3, 1)
 
+    def _fir_store(self, op, xc, dst, B, C, H, W, Hin, Win):
+        if op.flags & (lib.F_UP | lib.F_DOWN):
+            k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
+            k2 = torch.outer(k1, k1) / 64.0
+            xx = xc.reshape(B * C, 1, Hin, Win)
+            if op.flags & lib.F_DOWN:
+                y = F.conv2d(F.pad(xx, (1, 1, 1, 1)), k2.view(1, 1, 4, 4))[:, :, ::2, ::2]
+            else:
+                z = xx.new_zeros(B * C, 1, 2 * Hin, 2 * Win)
+                z[:, :, ::2, ::2] = xx
+                y = F.conv2d(F.pad(z, (2, 1, 2, 1)), (k2 * 4).view(1, 1, 4, 4))
+            xc = y.reshape(B, C, H, W)
+        self.get(dst, B * H * W * C).copy_(xc.permute(0, 2, 3, 1).reshape(-1))
+
     # -- ops ----------------------------------------------------------------------------------------
     def exec(self, op):
         k = op.kind
@@ -125,8 +139,11 @@ class Interpreter:
                 out[:, c, :, 0] = seg.sum(1)
                 out[:, c, :, 1] = (seg * seg).sum(1)
         elif k == lib.OP_GN_FINALIZE:
-            C, nchunk, cg = op.C0, op.i0, op.i1
-            part = self.get(op.src0, B * nchunk * C * 2, torch.float64).view(B, nchunk, C, 2)
+            C, nchunk, cg = op.C0 + op.C1, op.i0, op.i1
+            part = self.get(op.src0, B * nchunk * op.C0 * 2, torch.float64).view(B, nchunk, op.C0, 2)
+            if op.C1 > 0:
+                p1 = self.get(op.src1, B * nchunk * op.C1 * 2, torch.float64).view(B, nchunk, op.C1, 2)
+                part = torch.cat([part, p1], dim=2)
             s = part.sum(1).view(B, C // cg, cg, 2).sum(2)          # [B, G, 2]
             cnt = H * W * cg
             mean = s[..., 0] / cnt
@@ -157,6 +174,8 @@ class Interpreter:
                 Hin, Win = H // 2, W // 2
             x = self._src(op, Hin, Win)
             C = op.C0 + op.C1
+            if op.dst2:
+                self._fir_store(op, x.permute(0, 3, 1, 2), op.dst2, B, C, H, W, Hin, Win)
             if op.aux0:
                 tab = self.get(op.aux0, B * C * 4).view(B, 1, 1, C, 4)
                 n = (x - tab[..., 0]) * tab[..., 1]
@@ -168,19 +187,7 @@ class Interpreter:
                 if op.flags & lib.F_ACT_OUT:
                     n = silu(n)
                 x = n
-            xc = x.permute(0, 3, 1, 2)
-            if op.flags & (lib.F_UP | lib.F_DOWN):
-                k1 = torch.tensor([1.0, 3.0, 3.0, 1.0])
-                k2 = torch.outer(k1, k1) / 64.0
-                xx = xc.reshape(B * C, 1, Hin, Win)
-                if op.flags & lib.F_DOWN:
-                    y = F.conv2d(F.pad(xx, (1, 1, 1, 1)), k2.view(1, 1, 4, 4))[:, :, ::2, ::2]
-                else:
-                    z = xx.new_zeros(B * C, 1, 2 * Hin, 2 * Win)
-                    z[:, :, ::2, ::2] = xx
-                    y = F.conv2d(F.pad(z, (2, 1, 2, 1)), (k2 * 4).view(1, 1, 4, 4))
-                xc = y.reshape(B, C, H, W)
-            self.get(op.dst, B * H * W * C).copy_(xc.permute(0, 2, 3, 1).reshape(-1))
+            self._fir_store(op, x.permute(0, 3, 1, 2), op.dst, B, C, H, W, Hin, Win)
         elif k in (lib.OP_CONV_SIMT, lib.OP_CONV_UMMA):
             x = self._src(op, H, W)
             C = op.C0 + op.C1

@@ -153,6 +153,16 @@ def test_groupnorm_table(B, H, C0, C1):
          mk(lib.OP_GN_FINALIZE, B, H=H, W=H, C0=C, i0=nchunk, i1=cg, f0=1e-5, src0=part, dst=tab, aux0=fd,
             i2=film.shape[1], i3=off, flags=lib.F_FILM)])
     assert (tab.cpu() - ref).abs().max().item() < 2e-5
+    if C1:
+        # per-tensor partials (what the lowering emits): one scan per tensor, finalize reads both arrays
+        pa = torch.zeros(B * nchunk * C0 * 2, dtype=torch.float64, device=DEV)
+        pb = torch.zeros(B * nchunk * C1 * 2, dtype=torch.float64, device=DEV)
+        tab2 = torch.zeros(B, C, 4, device=DEV)
+        run([mk(lib.OP_GN_PARTIAL, B, H=H, W=H, C0=C0, i0=nchunk, src0=x0d, dst=pa),
+             mk(lib.OP_GN_PARTIAL, B, H=H, W=H, C0=C1, i0=nchunk, src0=x1d, dst=pb),
+             mk(lib.OP_GN_FINALIZE, B, H=H, W=H, C0=C0, C1=C1, i0=nchunk, i1=cg, f0=1e-5, src0=pa, src1=pb, dst=tab2,
+                aux0=fd, i2=film.shape[1], i3=off, flags=lib.F_FILM)])
+        assert torch.equal(tab2, tab)
 
 
 @pytest.mark.parametrize("mode", ["none", "down", "up"])
@@ -183,9 +193,11 @@ def test_apply_fir(mode, spade):
     x0d, x1d, td, gd, bd = d(x0), d(x1), d(tab), d(gam), d(bet)
     o1 = torch.zeros(B, H, H, C, device=DEV)
     o2 = torch.zeros(B, H, H, C, device=DEV)
+    o3 = torch.zeros(B, H, H, C, device=DEV)
     run([mk(lib.OP_APPLY, B, H=H, W=H, C0=C0, C1=C1, src0=x0d, src1=x1d, aux0=td, aux1=gd if spade else None,
-            aux2=bd if spade else None, dst=o1, flags=lib.F_ACT_OUT | fl),
+            aux2=bd if spade else None, dst=o1, dst2=o3, flags=lib.F_ACT_OUT | fl),      # fused dual output
          mk(lib.OP_APPLY, B, H=H, W=H, C0=C0, C1=C1, src0=x0d, src1=x1d, dst=o2, flags=fl)])
+    assert torch.equal(o2, o3)
     assert (o1.cpu() - n.permute(0, 2, 3, 1)).abs().max().item() < 1e-5
     assert (o2.cpu() - raw.permute(0, 2, 3, 1)).abs().max().item() < 1e-5
 
