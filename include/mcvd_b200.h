@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCVD_ABI_VERSION 1
+#define MCVD_ABI_VERSION 2
 
 /* ---- op kinds ------------------------------------------------------------------------------- */
 enum {
@@ -92,7 +92,11 @@ enum {
   /* 3x3 / 1x1 convolution on the 5th-gen tensor cores (tcgen05.mma kind::f16, fp16 hi/lo split of
    * both operands, fp32 accumulation in TMEM), with the GroupNorm/FiLM/SiLU transform of the input
    * fused into the shared-memory staging.  Same semantics as MCVD_OP_CONV_SIMT; see
-   * mcvd_b200/csrc/conv_umma.cu. */
+   * mcvd_b200/csrc/conv_umma.cu.  aux1 = norm table of (src0|src1) or NULL; i1 = n tile; i2 = accumulators
+   * per tile (0 = auto); f1 = weight un-scale.  Optional second K-segment (src2|src3 with C2|C3 channels, RAW,
+   * centre tap only, weights appended per n-tile): the 1x1 shortcut Conv_2(x) of ResnetBlockBigGANpp
+   * (layerspp.py:618-619) accumulated into the same TMEM tile as Conv_1, so
+   * dst = f0 * (Conv_1(act(norm(h))) + Conv_2(x) + bias + residual) in ONE kernel. */
   MCVD_OP_CONV_UMMA = 12,
   /* final 3x3 conv with tiny Cout (<= 16) and fused input norm: conv3x3(SiLU(GN(x))) of
    * ncsnpp_more.py:375-379; aux0 = float4 norm table or NULL. */
@@ -132,6 +136,10 @@ typedef struct McvdOp {
   const void* aux2;
   void* dst;
   void* dst2;
+  /* second K-segment of MCVD_OP_CONV_UMMA (fused 1x1 shortcut, see the kind's comment); NULL/0 otherwise */
+  const void* src2;
+  const void* src3;
+  int32_t C2, C3;
 } McvdOp;
 
 /* Library / ABI identification. */

@@ -48,6 +48,9 @@ constexpr int TAB_NB = 8;       // images whose norm-table rows are staged in sm
 struct UmmaArgs {
   const float* s0;
   const float* s1;
+  const float* s2;       // second K-segment (fused 1x1 shortcut): raw sources, centre tap only
+  const float* s3;
+  int C2, C3, nKB0;      // nKB0 = K-blocks of the first segment; K-blocks >= nKB0 belong to the second
   const __half* wpk;     // packed weights (see k_pack_weights)
   const float* bias;
   const float* res;
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       tb[32 + c] = treg.y * treg.z;
       tb[64 + c] = treg.w;
     };
-    auto emit = [&](const float4* raw, int pix, int bidx, int h, const float4* tsm, uint8_t* hi_base, uint8_t* lo_base) {
+    auto emit = [&](const float4* raw, int pix, int bidx, int h, const float4* tsm, uint8_t* hi_base, uint8_t* lo_base,
+                    bool use_tab) {
       if (pix == -2) return;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
@@ -176,7 +180,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
           if (pix >= 0) {
             float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
                           raw[2 * ch + 1].x, raw[2 * ch + 1].y, raw[2 * ch + 1].z, raw[2 * ch + 1].w};
-            if (has_tab) {
+            if (use_tab) {
               const float* tb = reinterpret_cast<const float*>(tsm) + bidx * 96 + ch * 8;
               const float4 m0 = *reinterpret_cast<const float4*>(tb), m1 = *reinterpret_cast<const float4*>(tb + 4);
               const float4 g0 = *reinterpret_cast<const float4*>(tb + 32), g1 = *reinterpret_cast<const float4*>(tb + 36);
@@ -227,8 +231,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         if (h < a.HP) { int b = tb0; ppix[i] = decode_pos(a, p0 - a.halo0 + h, b); pb[i] = b - tb0; }
       }
       auto src_of = [&](int kb, const float*& src, int& cs, int& cc0) {
-        const int c0 = kb * a.KB;
-        if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
+        if (kb < a.nKB0) {
+          const int c0 = kb * a.KB;
+          if (c0 < a.C0) { src = a.s0; cs = a.C0; cc0 = c0; } else { src = a.s1; cs = a.C1; cc0 = c0 - a.C0; }
+        } else {
+          const int c0 = (kb - a.nKB0) * a.KB;
+          if (c0 < a.C2) { src = a.s2; cs = a.C2; cc0 = c0; } else { src = a.s3; cs = a.C3; cc0 = c0 - a.C2; }
+        }
       };
       // one K-block: `cur` already holds (or receives) this K-block's channels of slab row 0; when `single`,
       // the NEXT K-block's channels are requested into `nxt` before the transform starts.
@@ -238,21 +247,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         src_of(kb, src, cs, cc0);
         if (!single) { fetch(cur, ppix[0], src, cs, cc0); fetch(nxt, ppix[1], src, cs, cc0); }
         else if (kb + 1 < a.nKB) { const float* s2; int cs2, cc2; src_of(kb + 1, s2, cs2, cc2); fetch(nxt, ppix[0], s2, cs2, cc2); }
-        if (kb + 1 < a.nKB) tab_load(tb0, kb + 1, treg); else if (more) tab_load(tb_next, 0, treg);
+        const bool tab_now = has_tab && kb < a.nKB0;                       // this K-block is normalised
+        const bool tab_nxt = has_tab && (kb + 1 < a.nKB0 || (kb + 1 == a.nKB && more));
+        if (tab_nxt) { if (kb + 1 < a.nKB0) tab_load(tb0, kb + 1, treg); else tab_load(tb_next, 0, treg); }
         DBG_T(tp);
         mbar_wait(A_EMPTY(st), ((g >> 1) & 1) ^ 1);
         DBG_ADD(1, tp, tid == 0);
-        if (has_tab) asm volatile("bar.sync 1, 256;" ::: "memory");   // this K-block's table staged by all
+        if (tab_now) asm volatile("bar.sync 1, 256;" ::: "memory");   // this K-block's table staged by all
         DBG_ADD(2, tp, tid == 0);
         uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
         uint8_t* lo_base = hi_base + a_half_bytes;
         const float4* tsm = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tab_s) + (size_t)st * TAB_NB * 96);
-        emit(cur, ppix[0], pb[0], tid, tsm, hi_base, lo_base);
+        emit(cur, ppix[0], pb[0], tid, tsm, hi_base, lo_base, tab_now);
         if (!single) {
-          emit(nxt, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base);
+          emit(nxt, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base, tab_now);
           if (a.HP > 2 * NPROD) {                        // 128-wide images: a third slab row for some threads
             fetch(nxt, ppix[2], src, cs, cc0);
-            emit(nxt, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base);
+            emit(nxt, ppix[2], pb[2], tid + 2 * NPROD, tsm, hi_base, lo_base, tab_now);
           }
         }
         DBG_ADD(3, tp, tid == 0);
@@ -261,7 +272,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         DBG_ADD(4, tp, tid == 0);
         // table of the NEXT K-block (possibly of the next tile) into the other buffer; everyone finished
         // reading that buffer before passing this K-block's bar.sync
-        if (kb + 1 < a.nKB || more) tab_store(g + 1, treg);
+        if (tab_nxt) {
+          // a raw (second-segment) K-block has no table barrier of its own: make sure every producer is done
+          // reading the buffer about to be overwritten
+          if (!tab_now) asm volatile("bar.sync 1, 256;" ::: "memory");
+          tab_store(g + 1, treg);
+        }
         ++g;
       };
       float4 rawA[8], rawB[8];
@@ -275,7 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     // =========================== weight loader ===========================
     if (elect_one()) {
       const uint32_t b0 = smem_u32(b_base);
-      const int per_tile = a.nKB * taps;
+      const int per_tile = a.nKB0 * taps + (a.nKB - a.nKB0);          // second segment: one (centre) tap per K-block
       int st = 0, ph = 1;
       for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wpk) + (size_t)(t % a.tiles_n) * per_tile * b_stage_bytes;
@@ -314,12 +330,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
           DBG_ADD(6, tm, true);
           tc_fence_after();
           const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
-          for (int tap = 0; tap < taps; ++tap) {
+          const int ntap = (kb < a.nKB0) ? taps : 1;
+          for (int tap = 0; tap < ntap; ++tap) {
             DBG_ADD(8, tm, true);
             mbar_wait(B_FULL(bst), bph);
             DBG_ADD(7, tm, true);
             tc_fence_after();
-            const int shift = (a.ks == 3) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
+            const int shift = (a.ks == 3 && kb < a.nKB0) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
             const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
             const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
             for (int s = 0; s < ksteps; ++s) {
@@ -503,13 +520,15 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.i0 == 1 || op.i0 == 3, "CONV_UMMA: kernel size %d unsupported", op.i0);
   UmmaArgs a;
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.wpk = (const __half*)op.w;
+  a.s2 = (const float*)op.src2; a.s3 = (const float*)op.src3; a.C2 = op.src2 ? op.C2 : 0; a.C3 = op.src3 ? op.C3 : 0;
   a.bias = (const float*)op.bias; a.res = (const float*)op.aux0; a.tab = (const float4*)op.aux1;
   a.dst = (float*)op.dst;
   a.dbg = (long long*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.Cout = op.Cout; a.ks = op.i0;
   a.NT = op.i1;
   a.KB = pick_kb(op.C0, op.C1);
-  MCVD_CHECK(a.KB != 0, "CONV_UMMA: input channels (%d,%d) must be multiples of 16", op.C0, op.C1);
+  if (a.C2 + a.C3 > 0 && pick_kb(a.C2, a.C3) < a.KB) a.KB = pick_kb(a.C2, a.C3);
+  MCVD_CHECK(a.KB != 0, "CONV_UMMA: input channels (%d,%d | %d,%d) must be multiples of 16", op.C0, op.C1, a.C2, a.C3);
   MCVD_CHECK(a.NT >= 16 && a.NT <= 256 && a.NT % 16 == 0 && op.Cout % a.NT == 0,
              "CONV_UMMA: n tile %d invalid for Cout %d", a.NT, op.Cout);
   if (a.ks == 3) { a.Wp = op.W + 1; a.Pimg = (op.H + 1) * (op.W + 1); }
@@ -535,7 +554,8 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.halo0 = (a.ks == 3) ? a.Wp + 1 : 0;
   a.HP = (MTOT + 2 * a.halo0 + 7) & ~7;
   MCVD_CHECK(a.HP <= 3 * NPROD, "CONV_UMMA: image width %d too large for the slab", op.W);
-  a.nKB = (op.C0 + op.C1) / a.KB;
+  a.nKB0 = (op.C0 + op.C1) / a.KB;
+  a.nKB = a.nKB0 + (a.C2 + a.C3) / a.KB;
   a.act_in = (op.flags & MCVD_F_ACT_IN) ? 1 : 0;
   a.act_out = (op.flags & MCVD_F_ACT_OUT) ? 1 : 0;
   a.wscale = op.f1; a.oscale = op.f0;

@@ -36,7 +36,7 @@ F_FILM = 1 << 4
 F_CLIP = 1 << 5
 F_PHILOX = 1 << 6
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = ["mcvd_abi_version", "mcvd_sizeof_op", "mcvd_last_error", "mcvd_device_arch", "mcvd_run_program",
            "mcvd_validate_program", "mcvd_count_launches", "mcvd_umma_pack_weights", "mcvd_umma_kblock"]
@@ -53,6 +53,7 @@ class McvdOp(C.Structure):
         ("src0", C.c_void_p), ("src1", C.c_void_p), ("w", C.c_void_p), ("bias", C.c_void_p),
         ("aux0", C.c_void_p), ("aux1", C.c_void_p), ("aux2", C.c_void_p),
         ("dst", C.c_void_p), ("dst2", C.c_void_p),
+        ("src2", C.c_void_p), ("src3", C.c_void_p), ("C2", C.c_int32), ("C3", C.c_int32),
     ]
 
 

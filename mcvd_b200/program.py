@@ -156,6 +156,27 @@ class Engine:
             raise RuntimeError(f"mcvd_b200 umma_pack_weights failed: {lib.last_error()}")
         return out, float(2.0 ** (-k))
 
+    def _pack_umma_fused(self, taps: torch.Tensor, taps_sc: torch.Tensor, nt: int, kb: int):
+        """main conv + 1x1 shortcut as one weight stream: per n-tile [main stages | shortcut stages]."""
+        if self.backend is not None:
+            both = torch.cat([taps.reshape(-1), taps_sc.reshape(-1)]).contiguous()
+            t, _ = self.backend.pack_umma(both, nt, kb)
+            return t, 1.0
+        amax = float(max(taps.abs().max().item(), taps_sc.abs().max().item()))
+        k = 0 if amax == 0.0 else int(math.floor(math.log2(512.0 / amax)))
+        k = max(-24, min(24, k))
+        n_nt = taps.shape[2] // nt
+        parts = []
+        for t in (taps, taps_sc):
+            T, I, O = t.shape
+            out = torch.empty(T * I * O * 4, device=t.device, dtype=torch.uint8)
+            with self._devctx():
+                rc = self.lib.mcvd_umma_pack_weights(t.data_ptr(), T, I, O, nt, kb, out.data_ptr(), k, self._stream())
+            if rc < 0:
+                raise RuntimeError(f"mcvd_b200 umma_pack_weights failed: {lib.last_error()}")
+            parts.append(out.view(n_nt, -1))
+        return torch.cat(parts, dim=1).contiguous().view(-1), float(2.0 ** (-k))
+
     # ------------------------------------------------------------------------------ lowering
     def program(self, B: int) -> Program:
         self.ensure_packed()
@@ -199,7 +220,7 @@ class Engine:
             o.kind = kind
             o.B = B
             for k, v in kw.items():
-                if k in ("src0", "src1", "w", "bias", "aux0", "aux1", "aux2", "dst", "dst2"):
+                if k in ("src0", "src1", "w", "bias", "aux0", "aux1", "aux2", "dst", "dst2", "src2", "src3"):
                     if isinstance(v, torch.Tensor):
                         v = v.data_ptr()
                     setattr(o, k, v)
@@ -213,8 +234,8 @@ class Engine:
 
         # ---- convolution (tensor-core or CUDA-core) -------------------------------------------
         def conv(ops, key, src: Src, H: int, cout: int, ks: int, wname: str, bname: str, residual=None,
-                 scale=1.0, tab=None, act_in=False, act_out=False, nin=False, wcat=None, bcat=None):
-            """dst = scale * (conv(act(norm(src))) + bias + residual)."""
+                 scale=1.0, tab=None, act_in=False, act_out=False, nin=False, wcat=None, bcat=None, shortcut=None):
+            """dst = scale * (conv(act(norm(src))) + bias + residual [+ conv1x1(shortcut src)])."""
             if wcat is not None:
                 taps, bias = wcat, bcat
             elif nin:
@@ -227,16 +248,33 @@ class Engine:
             dst = f32(B, H, H, cout)
             kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
             nt = _pick_nt(cout) if cout % 16 == 0 else 0
+            sc = None
+            if shortcut is not None:                       # (Src, wname, bname): 1x1 Conv_2 of the skip branch
+                sc_src, sc_w, sc_b = shortcut
+                kb2 = lib.umma_kblock(sc_src.c0, sc_src.c1) if kb else 0
+                if kb and nt and kb2 and (tab is None or H >= 8):
+                    kb = min(kb, kb2)
+                    sc = (sc_src, self._conv_taps(sd(sc_w)))
+                    bias = keep((bias + sd(sc_b).float()).contiguous())
+                else:                                       # not fusable: separate 1x1 conv, added as residual
+                    assert residual is None
+                    residual = conv(ops, key + ".sc", sc_src, H, cout, 1, sc_w, sc_b)
             if kb and nt and (tab is None or H >= 8):      # fused-norm slab stages <= 8 images' table rows
-                pk = (key, "umma", nt, kb)
+                pk = (key, "umma", nt, kb, sc is not None)
                 if pk not in self.packed:
-                    self.packed[pk] = self._pack_umma(taps, nt, kb)
+                    if sc is None:
+                        self.packed[pk] = self._pack_umma(taps, nt, kb)
+                    else:                                  # both segments share one power-of-two scale
+                        self.packed[pk] = self._pack_umma_fused(taps, sc[1], nt, kb)
                 wp, wscale = self.packed[pk]
                 nacc = 0                       # auto: chosen by the launcher (TMEM double-buffering, grid fill)
                 fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
+                kw2 = {}
+                if sc is not None:
+                    kw2 = dict(src2=sc[0].t0, src3=sc[0].t1, C2=sc[0].c0, C3=sc[0].c1)
                 emit(ops, lib.OP_CONV_UMMA, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=nt, i2=nacc,
                      f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, aux1=tab,
-                     dst=dst, flags=fl)
+                     dst=dst, flags=fl, **kw2)
                 P.n_umma += 1
                 return dst
             if tab is not None:
@@ -367,8 +405,9 @@ class Engine:
                 h = conv(step, pre + "Conv_0", src, H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias", tab=tab0,
                          act_in=True)
             tab1 = norm_table(step, Src(h, Cout), H, eps, film_off=ms.film_off[1])
-            if ms.has_shortcut:
-                res = conv(step, pre + "Conv_2", sc_src, H, Cout, 1, pre + "Conv_2.weight", pre + "Conv_2.bias")
+            shortcut = res = None
+            if ms.has_shortcut:                      # Conv_2 rides along Conv_1 as a second K-segment
+                shortcut = (sc_src, pre + "Conv_2.weight", pre + "Conv_2.bias")
             else:
                 assert src.t1 is None and src.c0 == Cout
                 res = src.t0
@@ -378,9 +417,9 @@ class Engine:
                 emit(step, lib.OP_APPLY, H=H, W=H, C0=Cout, src0=h, aux0=tab1, aux1=g1, aux2=b1, dst=a1,
                      flags=lib.F_ACT_OUT)
                 return conv(step, pre + "Conv_1", Src(a1, Cout), H, Cout, 3, pre + "Conv_1.weight",
-                            pre + "Conv_1.bias", residual=res, scale=INV_SQRT2)
+                            pre + "Conv_1.bias", residual=res, scale=INV_SQRT2, shortcut=shortcut)
             return conv(step, pre + "Conv_1", Src(h, Cout), H, Cout, 3, pre + "Conv_1.weight", pre + "Conv_1.bias",
-                        residual=res, scale=INV_SQRT2, tab=tab1, act_in=True)
+                        residual=res, scale=INV_SQRT2, tab=tab1, act_in=True, shortcut=shortcut)
 
         def attnblock(ms: arch.ModSpec, x: torch.Tensor) -> torch.Tensor:
             pre = f"unet.all_modules.{ms.idx}."

@@ -203,6 +203,17 @@ class Interpreter:
                 OP = op.i1
                 scale, wscale = float(op.f0), 1.0
             y = self._conv(op, x, OP) * wscale
+            if k == lib.OP_CONV_UMMA and op.src2:
+                # second K-segment: raw 1x1 conv of (src2|src3); its [1][C2+C3][Cout] weights follow the main ones
+                Hs = H
+                a2 = self.get(op.src2, B * Hs * W * op.C2).view(B, Hs, W, op.C2)
+                if op.C3 > 0:
+                    a2 = torch.cat([a2, self.get(op.src3, B * Hs * W * op.C3).view(B, Hs, W, op.C3)], 3)
+                Cs = op.C2 + op.C3
+                w_all = self.get(op.w)
+                n_main = op.i0 * op.i0 * C * op.Cout
+                w2 = w_all[n_main:n_main + Cs * op.Cout].view(Cs, op.Cout)
+                y = y + torch.einsum("bhwc,co->bhwo", a2, w2)
             y = y + self.get(op.bias, op.Cout)
             if op.aux0:
                 y = y + self.get(op.aux0, B * H * W * op.Cout).view(B, H, W, op.Cout)

@@ -296,3 +296,50 @@ def test_resize_and_smalln():
     run([mk(lib.OP_CONV_SMALLN, B, H=S, W=S, C0=Cin, Cout=Cout, i1=8, src0=xd, w=wd, bias=bd, aux0=td, dst=out,
             flags=lib.F_ACT_OUT)])
     assert (out.cpu() - ref).abs().max().item() < 2e-5
+
+
+FUSED_CASES = [
+    # B, H, Cmain, Cout, Cs0, Cs1   (main: 3x3 on act(norm(h)); shortcut: raw 1x1 on (x0|x1), fused as 2nd K-segment)
+    (2, 16, 64, 64, 32, 0),        # shortcut of a single K-block (table-buffer hazard case)
+    (2, 8, 96, 96, 96, 96),        # concat shortcut source
+    (3, 16, 48, 48, 48, 48),       # KB = 16
+    (2, 32, 32, 96, 64, 0),
+    (2, 8, 128, 256, 128, 64),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_conv_umma_fused_shortcut(case):
+    B, H, Cm, Cout, Cs0, Cs1 = case
+    Cs = Cs0 + Cs1
+    h = rnd(B, H, H, Cm, seed=1)
+    x0 = rnd(B, H, H, Cs0, seed=2)
+    x1 = rnd(B, H, H, Cs1, seed=3) if Cs1 else None
+    w1 = rnd(Cout, Cm, 3, 3, seed=4) / math.sqrt(9 * Cm)
+    w2 = rnd(Cout, Cs, 1, 1, seed=5) / math.sqrt(Cs)
+    b1, b2 = rnd(Cout, seed=6) * 0.1, rnd(Cout, seed=7) * 0.1
+    tab = make_table(B, Cm)
+    xs = x0 if x1 is None else torch.cat([x0, x1], 3)
+    ref = conv_ref(ref_norm(h, tab, True), w1, b1, None, 1.0, False) + conv_ref(xs, w2, b2, None, 1.0, False)
+    ref = ref * 0.7071
+    kb = min(lib.umma_kblock(Cm, 0), lib.umma_kblock(Cs0, Cs1))
+    nt = max(dd for dd in range(16, 257, 16) if Cout % dd == 0)
+    t1, t2 = taps_of(w1).to(DEV), taps_of(w2).to(DEV)
+    k = int(math.floor(math.log2(512.0 / float(max(t1.abs().max(), t2.abs().max())))))
+    parts = []
+    for t in (t1, t2):
+        pk = torch.empty(t.numel() * 4, dtype=torch.uint8, device=DEV)
+        rc = lib.load().mcvd_umma_pack_weights(t.data_ptr(), t.shape[0], t.shape[1], Cout, nt, kb, pk.data_ptr(), k,
+                                               torch.cuda.current_stream().cuda_stream)
+        assert rc > 0, lib.last_error()
+        parts.append(pk.view(Cout // nt, -1))
+    wpk = torch.cat(parts, 1).contiguous().view(-1)
+    d = lambda t: None if t is None else t.to(DEV).contiguous()
+    hd, x0d, x1d, td, bd = d(h), d(x0), d(x1), d(tab), d(b1 + b2)
+    out = torch.zeros(B, H, H, Cout, device=DEV)
+    for nacc in (0, 1, 2):
+        out.zero_()
+        run([mk(lib.OP_CONV_UMMA, B, H=H, W=H, C0=Cm, Cout=Cout, i0=3, i1=nt, i2=nacc, f0=0.7071, f1=2.0 ** (-k),
+                src0=hd, w=wpk, bias=bd, aux1=td, dst=out, flags=lib.F_ACT_IN, src2=x0d, src3=x1d, C2=Cs0, C3=Cs1)])
+        err = (out.cpu() - ref).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref.abs().max().item()), (case, nacc, err)
