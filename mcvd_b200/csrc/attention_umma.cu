@@ -51,7 +51,7 @@ __device__ __forceinline__ void split8(const float v[8], uint4& hv, uint4& lv) {
 template <int D>
 __device__ __forceinline__ void stage_rows(uint8_t* hi, uint8_t* lo, const float* src, long long stride, int rows,
                                            int valid_rows, int tid, int nthreads) {
-  constexpr int U = 4;                                   // units in flight per thread (8 x LDG.128)
+  constexpr int U = 6;                                   // units in flight per thread (12 x LDG.128)
   const int units = (D / 8) * rows;
   for (int u0 = tid; u0 < units; u0 += nthreads * U) {
     float4 va[U], vb[U];
@@ -203,28 +203,37 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       fence_proxy_async();
       mbar_arrive(K_FULL);
       if (j > 0) mbar_wait(O_FULL, (j - 1) & 1);            // PV_{j-1} done: V buffer free
-      // V^T: rows = channels, k = keys.  unit = (key chunk kc, channel c); lanes walk channels
+      // V^T: rows = channels, k = keys.  unit = (key chunk kc of 8 keys, 4 channels): 8 x LDG.128 (one per
+      // key, 4 channels each), transposed in registers into 4 rows of 8 keys; 2 units (16 loads) in flight.
       const float* vsrc = base + 2 * a.C + (long long)k0 * C3;
-      for (int u0 = st; u0 < (KT / 8) * D; u0 += 256) {
-        float v[2][8];
+      constexpr int C4 = D / 4;
+      const int vunits = (KT / 8) * C4;
+      for (int u0 = st; u0 < vunits; u0 += 256) {
+        float4 ld[2][8];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int u = u0 + i * 128;
-          const int kc = u / D, c = u - kc * D;
+          const int kc = u / C4, c4 = u - kc * C4;
 #pragma unroll
           for (int e = 0; e < 8; ++e)
-            v[i][e] = (u < (KT / 8) * D) ? __ldg(vsrc + (long long)(kc * 8 + e) * C3 + c) : 0.f;
+            ld[i][e] = (u < vunits) ? __ldg(reinterpret_cast<const float4*>(vsrc + (long long)(kc * 8 + e) * C3) + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int u = u0 + i * 128;
-          if (u < (KT / 8) * D) {
-            const int kc = u / D, c = u - kc * D;
+          if (u < vunits) {
+            const int kc = u / C4, c4 = u - kc * C4;
+            const float r0[8] = {ld[i][0].x, ld[i][1].x, ld[i][2].x, ld[i][3].x, ld[i][4].x, ld[i][5].x, ld[i][6].x, ld[i][7].x};
+            const float r1[8] = {ld[i][0].y, ld[i][1].y, ld[i][2].y, ld[i][3].y, ld[i][4].y, ld[i][5].y, ld[i][6].y, ld[i][7].y};
+            const float r2[8] = {ld[i][0].z, ld[i][1].z, ld[i][2].z, ld[i][3].z, ld[i][4].z, ld[i][5].z, ld[i][6].z, ld[i][7].z};
+            const float r3[8] = {ld[i][0].w, ld[i][1].w, ld[i][2].w, ld[i][3].w, ld[i][4].w, ld[i][5].w, ld[i][6].w, ld[i][7].w};
             uint4 hv, lv;
-            split8(v[i], hv, lv);
-            const size_t off = ((size_t)kc * D + c) * 16;
-            *reinterpret_cast<uint4*>(vh + off) = hv;
-            *reinterpret_cast<uint4*>(vl + off) = lv;
+            const size_t off = ((size_t)kc * D + c4 * 4) * 16;
+            split8(r0, hv, lv); *reinterpret_cast<uint4*>(vh + off) = hv;      *reinterpret_cast<uint4*>(vl + off) = lv;
+            split8(r1, hv, lv); *reinterpret_cast<uint4*>(vh + off + 16) = hv; *reinterpret_cast<uint4*>(vl + off + 16) = lv;
+            split8(r2, hv, lv); *reinterpret_cast<uint4*>(vh + off + 32) = hv; *reinterpret_cast<uint4*>(vl + off + 32) = lv;
+            split8(r3, hv, lv); *reinterpret_cast<uint4*>(vh + off + 48) = hv; *reinterpret_cast<uint4*>(vl + off + 48) = lv;
           }
         }
       }
