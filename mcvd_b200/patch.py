@@ -44,11 +44,10 @@ def install(verbose: bool = True):
         @functools.wraps(ref_fn)
         def sampler(x_mod, scorenet, *a, **kw):
             net = scorenet.module if hasattr(scorenet, "module") else scorenet
-            use_fast = (isinstance(net, fast_model.UNetMore_DDPM) and x_mod.is_cuda and not kw.get("gamma", False)
-                        and not (kw.get("t_min", -1) or -1) > 0)
+            use_fast = isinstance(net, fast_model.UNetMore_DDPM) and x_mod.is_cuda and not kw.get("gamma", False)
             if isinstance(net, fast_model.UNetMore_DDPM) and not use_fast:
                 raise RuntimeError("mcvd_b200 module used with sampler options the fast path does not cover "
-                                   "(gamma / init_prev_t); build the reference model for those")
+                                   "(gamma); build the reference model for those")
             return (fast_fn if use_fast else ref_fn)(x_mod, scorenet, *a, **kw)
         return sampler
 

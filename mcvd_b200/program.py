@@ -505,6 +505,7 @@ class Engine:
                 last_src = an
             emit(step, lib.OP_CONV_SIMT, H=S, W=S, C0=cur_c, Cout=ns.out_ch, i0=3, i1=coutp, f0=1.0, src0=last_src,
                  w=wlp, bias=bl, dst=P.eps_nhwc)
+        P.eps_nhwc.zero_()           # read (times 0) by the warm-start noising update before the first network call
         P.n_net_ops = len(step)
 
         P.cond_arr = lib.make_ops(cnd) if cnd else None

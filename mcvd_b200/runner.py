@@ -102,8 +102,13 @@ def video_gen_clips(config, scorenet, cond: torch.Tensor, num_frames_pred: Optio
     B = cond.shape[0]
     shape = (B, C * F, S, S)
     preds = []
+    warm = (getattr(config.sampling, "init_prev_t", -1) or -1) > 0
+    gen = None
     for i in range(n_iter):
-        x_T = init_fn(i, shape) if init_fn is not None else torch.randn(shape, device=cond.device)
+        if warm and i > 0:
+            x_T = gen                                    # init_prev_t > 0: restart from the previous block (:1513)
+        else:
+            x_T = init_fn(i, shape) if init_fn is not None else torch.randn(shape, device=cond.device)
         extra = {}
         if noise_fn is not None:
             extra["noise_list"] = noise_fn(i)

@@ -117,7 +117,7 @@ def _log_line(tag, i, L, grad, x, c_alpha, verbose, log):
 def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, denoise=True, subsample_steps=None,
                  same_noise=False, noise_val=None, frac_steps=None, verbose=False, log=False, clip_before=True,
                  t_min=-1, gamma=False, noise_list: Optional[List[torch.Tensor]] = None, philox_seed=None,
-                 clip_offset=0, **kwargs):
+                 clip_offset=0, warm_noise: Optional[torch.Tensor] = None, **kwargs):
     """Reference ``ddpm_sampler`` (models/__init__.py:207-340).
 
     Extensions (keyword-only in practice): ``noise_list`` = per-step injected noise (L-1 tensors) for
@@ -127,8 +127,7 @@ def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, 
     """
     if gamma:
         raise NotImplementedError("gamma=True is not accelerated (reference models/__init__.py:214,319-322)")
-    if t_min is not None and t_min > 0:
-        raise NotImplementedError("init_prev_t warm start is not accelerated yet")
+    t_min = -1 if t_min is None else t_min
     lp = _Loop(x_mod, scorenet, cond)
     try:
         steps, alphas, alphas_prev, betas = _schedule(lp.net, subsample_steps)
@@ -139,7 +138,14 @@ def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, 
             noise_val = x_mod.detach().clone()
         L = len(steps)
         images = []
+        x_transf = False
         for i, step in enumerate(steps):
+            if step < t_min * len(alphas):                                      # :269-270 (init_prev_t warm start)
+                continue
+            if not x_transf and t_min > 0:                                      # :272-279: noise x to this level
+                z0 = warm_noise if warm_noise is not None else torch.randn(lp.P.noise.shape, device=lp.dev)
+                lp.update(0.0, 0.0, 0.0, alphas[i].sqrt().item(), 0.0, (1 - alphas[i]).sqrt().item(), False, noise=z0)
+            x_transf = True
             c_beta, c_alpha, c_alpha_prev = betas[i], alphas[i], alphas_prev[i]
             lp.eps(float(step))                                                 # :283-284
             k0 = 1 / c_alpha.sqrt()                                             # :287
@@ -187,18 +193,24 @@ def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, 
 
 @torch.no_grad()
 def ddim_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, subsample_steps=None, verbose=False,
-                 log=True, clip_before=True, t_min=-1, gamma=False, **kwargs):
+                 log=True, clip_before=True, t_min=-1, gamma=False, warm_noise: Optional[torch.Tensor] = None, **kwargs):
     """Reference ``ddim_sampler`` (models/__init__.py:103-203): x = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps."""
     if gamma:
         raise NotImplementedError("gamma=True is not accelerated")
-    if t_min is not None and t_min > 0:
-        raise NotImplementedError("init_prev_t warm start is not accelerated yet")
+    t_min = -1 if t_min is None else t_min
     lp = _Loop(x_mod, scorenet, cond)
     try:
         steps, alphas, alphas_prev, betas = _schedule(lp.net, subsample_steps)
         L = len(steps)
         images = []
+        x_transf = False
         for i, step in enumerate(steps):
+            if step < t_min * len(alphas):                                           # :143-144
+                continue
+            if not x_transf and t_min > 0:                                           # :146-153
+                z0 = warm_noise if warm_noise is not None else torch.randn(lp.P.noise.shape, device=lp.dev)
+                lp.update(0.0, 0.0, 0.0, alphas[i].sqrt().item(), 0.0, (1 - alphas[i]).sqrt().item(), False, noise=z0)
+            x_transf = True
             c_alpha, c_alpha_prev = alphas[i], alphas_prev[i]
             lp.eps(float(step))
             lp.update((1 / c_alpha.sqrt()).item(), (1 - c_alpha).sqrt().item(), c_alpha_prev.sqrt().item(), 0.0,

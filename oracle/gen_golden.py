@@ -50,6 +50,11 @@ def gen(name):
         with mock.patch("torch.randn_like", lambda _x: next(it)):
             out["ddpm"] = ddpm(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=L,
                                clip_before=True, log=False, verbose=False)[0].numpy()
+        # init_prev_t warm start (t_min > 0): first randn_like call is the re-noising, then the per-step noise
+        it2 = iter([detfill.normal("warm", x.shape)] + zs)
+        with mock.patch("torch.randn_like", lambda _x: next(it2)):
+            out["ddpm_tmin"] = ddpm(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=L,
+                                    clip_before=True, log=False, verbose=False, t_min=0.35)[0].numpy()
         out["ddim"] = ddim(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=L,
                            clip_before=True, log=False, verbose=False)[0].numpy()
         out["fpndm"] = fpndm(x.clone(), net, cond=cond, final_only=True, subsample_steps=L,

@@ -286,16 +286,27 @@ def _subsample(sched, subsample_steps):
 
 @torch.no_grad()
 def ddpm_sample(net, sched, x: Tensor, cond=None, subsample_steps=None, denoise=True, clip_before=True,
-                noise: Optional[List[Tensor]] = None, just_beta=False, final_only=True):
+                noise: Optional[List[Tensor]] = None, just_beta=False, final_only=True, t_min=-1,
+                warm_noise: Optional[Tensor] = None):
     """ddpm_sampler, ``models/__init__.py:207-340`` (t_min<=0, gamma=False path).
 
     ``net(x, labels, cond)`` is the score network.  ``noise`` is a list with one tensor per step that
     adds noise (L-1 entries); when None, torch.randn_like is used as in the reference (:324).
+    ``t_min > 0`` is the ``init_prev_t`` warm start (:269-280): steps with ``step < t_min * len(alphas)`` are
+    skipped (``alphas`` being the SUBSAMPLED schedule, as written) and x is first noised to the level of
+    the first kept step with ``warm_noise``.
     """
     steps, alphas, alphas_prev, betas = _subsample(sched, subsample_steps)
     L = len(steps)
     images = []
+    x_transf = False
     for i, step in enumerate(steps):
+        if step < t_min * len(alphas):                                                   # :269-270
+            continue
+        if not x_transf and t_min > 0:                                                   # :272-279
+            z0 = warm_noise if warm_noise is not None else torch.randn_like(x)
+            x = alphas[i].sqrt() * x + (1 - alphas[i]).sqrt() * z0
+        x_transf = True
         c_beta, c_alpha, c_alpha_prev = betas[i], alphas[i], alphas_prev[i]
         labels = (step * torch.ones(x.shape[0])).long()                                  # :283
         grad = net(x, labels, cond)                                                      # :284

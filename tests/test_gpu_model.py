@@ -128,3 +128,22 @@ def test_state_dict_reload_repacks_weights():
     assert not torch.allclose(a, b)
     bad, mx, _ = allclose_report(b.cpu(), ref, RTOL, ATOL)
     assert bad == 0, mx
+
+
+def test_warm_start_t_min_vs_reference_golden():
+    name = "tiny_spade"
+    cfg, net, sd = gpu_module(name)
+    B, L = cfg.bench_batch, cfg.sampling.subsample
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    zs = step_noise(x.shape, L)
+    steps = list(range(0, 1000, 1000 // L))
+    kept = [i for i, s_ in enumerate(steps) if not (s_ < 0.35 * L)]
+    aligned = [None] * (L - 1)
+    for k, i in enumerate(kept[:-1]):
+        aligned[i] = zs[k].to(DEV)
+    out = samplers.ddpm_sampler(x.to(DEV), net, cond=cond.to(DEV), final_only=True, denoise=True, subsample_steps=L,
+                                clip_before=True, noise_list=aligned, t_min=0.35,
+                                warm_noise=detfill.normal("warm", x.shape).to(DEV))
+    g = golden(name)
+    to01 = lambda a: ((a + 1) / 2).clamp(0, 1)
+    assert O.psnr01(to01(out[0].cpu()), to01(torch.from_numpy(g["ddpm_tmin"]))) >= 50.0

@@ -76,3 +76,31 @@ def test_video_gen_loop_lowering():
     ref = torch.from_numpy(g["video"])
     assert vid.shape == ref.shape
     assert O.psnr01(vid, ref) > 50.0
+
+
+def test_warm_start_t_min_matches_reference_golden_and_oracle():
+    """init_prev_t warm start (t_min > 0), replicated as the reference writes it (models/__init__.py:269-280)."""
+    name = "tiny"
+    cfg, net, sd = cpu_module(name, "umma")
+    B, L = cfg.bench_batch, cfg.sampling.subsample
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    zs = step_noise(x.shape, L)
+    warm = detfill.normal("warm", x.shape)
+    out = samplers.ddpm_sampler(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=L,
+                                clip_before=True, noise_list=zs, t_min=0.35, warm_noise=warm)
+    g = golden(name)
+    # the reference's randn_like sequence is [warm, z0, z1, ...] consumed in order, so step i draws zs[k] with k
+    # counting only the steps that were not skipped
+    sched = O.make_schedule(cfg)
+    fn = lambda xx, tt, cc: O.unet_forward(cfg, sd, xx, tt, cc)
+    steps = list(range(0, 1000, 1000 // L))
+    kept = [i for i, s_ in enumerate(steps) if not (s_ < 0.35 * L)]
+    # our sampler indexes noise_list by step index i; build the list the reference's consumption order implies
+    aligned = [None] * (L - 1)
+    for k, i in enumerate(kept[:-1]):
+        aligned[i] = zs[k]
+    out = samplers.ddpm_sampler(x.clone(), net, cond=cond, final_only=True, denoise=True, subsample_steps=L,
+                                clip_before=True, noise_list=aligned, t_min=0.35, warm_noise=warm)
+    assert max_err(out[0], torch.from_numpy(g["ddpm_tmin"])) < 2e-3
+    ref = O.ddpm_sample(fn, sched, x.clone(), cond, L, True, True, noise=aligned, t_min=0.35, warm_noise=warm)
+    assert max_err(out[0], ref[0]) < 2e-3
