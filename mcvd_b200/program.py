@@ -63,6 +63,7 @@ class Program:
         self.update_arr = None
         self.n_umma = 0
         self.n_simt = 0
+        self.graph = None                    # CUDA graph of step_ops (uniform-timestep variant), captured lazily
         self.temb_idx: List[int] = []        # step ops of the time-embedding MLP + fused FiLM projection
         self.film_fin_idx: List[int] = []    # GN_FINALIZE ops that read the FiLM table
         self.uniform_t = False
@@ -88,6 +89,7 @@ class Engine:
                                    f"{lib.last_error()})")
         self.conv_mode = os.environ.get("MCVD_CONV", "umma").lower()       # 'umma' | 'simt'
         self.attn_mode = os.environ.get("MCVD_ATTN", "umma").lower()        # 'umma' | 'simt'
+        self.use_graph = os.environ.get("MCVD_GRAPH", "1") != "0"
         self.packed: Dict[str, object] = {}
         self.packed_version = None
         self.programs: Dict[int, Program] = {}
@@ -544,6 +546,21 @@ class Engine:
     def run_step(self, P: Program):
         self._run(P.step_arr, len(P.step_ops))
 
+    def run_step_graphed(self, P: Program):
+        """One network evaluation replayed from a CUDA graph (the ~260 launches of a forward are captured once
+        per program; the timestep lives in device memory, so one graph serves every step).  Only the
+        uniform-timestep variant is captured -- that is what every sampler step uses."""
+        if self.backend is not None or not self.use_graph or not P.uniform_t:
+            return self.run_step(P)
+        if P.graph is None:
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            self.run_step(P)                                   # warm (module loading, func attributes) outside capture
+            with torch.cuda.graph(g):
+                self.run_step(P)
+            P.graph = g
+        P.graph.replay()
+
     def set_uniform_t(self, P: Program, uniform: bool):
         """All clips share one timestep (every sampler step): evaluate the time-embedding MLP and the fused
         FiLM projection for ONE row and let every GN_FINALIZE read it with batch stride 0 -- B x fewer
@@ -555,6 +572,7 @@ class Engine:
         for i in P.film_fin_idx:
             P.step_arr[i].i2 = 0 if uniform else self.spec.film_total
         P.uniform_t = uniform
+        P.graph = None                 # kernel arguments changed: a captured graph would replay stale ones
 
     def set_inputs(self, P: Program, x=None, t=None, cond=None):
         if x is not None:

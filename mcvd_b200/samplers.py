@@ -72,7 +72,7 @@ class _Loop:
     def eps(self, t):
         """eps = net(x_state, t, cond) into P.eps_nhwc (x_state = P.x_in)."""
         self.eng.set_inputs(self.P, t=t)
-        self.eng.run_step(self.P)
+        self.eng.run_step_graphed(self.P)
         self.launches += len(self.P.step_ops)
 
     def update(self, k0, k1, ca, cb, cc, sigma, clip, noise=None, philox=None, step=0):
