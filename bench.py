@@ -367,6 +367,23 @@ def roofline(net, P, B, cfg, pk, pk_src):
            "peak_source": f"{pk_src} cuBLAS bf16 sustained (MEASURED_PEAKS.json)", "traffic": None,
            "per_kind": per_kind, "forward_ms_sum_of_kernels": total_ms}
     if lib.OP_CONV_UMMA in tot:
+        n_umma = tot[lib.OP_CONV_UMMA][1] // reps
+        # algorithmic HBM bytes of the kernel: every conv reads its input(s) and writes its output once (fp32),
+        # plus residual and the packed weights
+        alg_bytes = 0.0
+        for op in P.step_ops:
+            if op.kind == lib.OP_CONV_UMMA:
+                px = op.B * op.H * op.W
+                alg_bytes += 4.0 * px * (op.C0 + op.C1 + op.C2 + op.C3 + op.Cout * (2 if op.aux0 else 1))
+                alg_bytes += 4.0 * op.Cout * ((op.C0 + op.C1) * op.i0 * op.i0 + op.C2 + op.C3)
+        tpath = os.path.join(ROOT, "profiles", "ncu_conv_umma_traffic.json")
+        if os.path.exists(tpath) and "cfg2" in getattr(cfg, "workload", "") and B == 64:
+            tj = json.load(open(tpath))
+            out["traffic"] = tj["dram_bytes_per_launch_mean"]
+            out["traffic_note"] = (f"mean dram__bytes_read+write per k_conv_umma launch from the committed ncu pass "
+                                   f"({tj['launches_per_forward']} launches, {tj['dram_bytes_per_forward'] / 1e9:.2f} GB per "
+                                   f"forward); algorithmic {alg_bytes / 1e9:.2f} GB per forward")
+        out["algorithmic_bytes_per_launch"] = alg_bytes / max(n_umma, 1)
         ms_umma = tot[lib.OP_CONV_UMMA][0] / reps
         ach = flops_umma / (ms_umma / 1e3) / 1e12
         out.update(kernel="k_conv_umma (tcgen05 implicit-GEMM conv, all conv launches of one forward)",
