@@ -414,4 +414,25 @@ def psnr_check(cfg, net, sd, dev, B=1, steps=None):
 
 
 if __name__ == "__main__":
-    main()
+    # stdout must carry exactly ONE JSON line: libraries (NCCL's version banner, torch warnings) write to fd 1
+    # behind Python's back, so fd 1 is pointed at stderr for the whole run and restored only for the result.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _buf = []
+    _print = print
+
+    def print(*a, **k):  # noqa: A001  (module-level print used by main() for the JSON line)
+        if k.get("file") in (None, sys.stdout):
+            _buf.append(" ".join(str(x) for x in a))
+        else:
+            _print(*a, **k)
+
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(_real_stdout, 1)
+        os.close(_real_stdout)
+        for line in _buf:
+            _print(line, flush=True)
