@@ -108,8 +108,13 @@ def workload(name: str) -> argparse.Namespace:
                    model=dict(ngf=48, ch_mult=[1, 2, 3], num_res_blocks=2, n_head_channels=48,
                               attn_resolutions=[8, 16]),
                    sampling=dict(subsample=20, num_frames_pred=5))
+    if name == "tiny128":   # 128-px, 5 levels (cityscapes-like topology): wide slabs, 3 slab rows per producer thread
+        return _mk(name, 2, data=dict(image_size=128, channels=3, num_frames=2, num_frames_cond=2),
+                   model=dict(ngf=32, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=1, n_head_channels=32,
+                              attn_resolutions=[8, 16, 32]),
+                   sampling=dict(subsample=5, num_frames_pred=4))
     raise KeyError(f"unknown workload {name!r}")
 
 
 ALL_WORKLOADS = ("cfg1", "cfg2", "cfg3", "cfg4", "cfg5")
-TEST_WORKLOADS = ("tiny", "tiny_spade", "tiny_rgb")
+TEST_WORKLOADS = ("tiny", "tiny_spade", "tiny_rgb", "tiny128")
