@@ -263,7 +263,7 @@ int launch_gn_finalize(const McvdOp& op, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------
 // apply: y = act( ((x - mean) * rstd [*(1+gamma)+beta]) * G + S ), optionally through the 4x4 FIR
-// up/down-sampler.  One thread = 4 consecutive channels of one OUTPUT pixel.
+// up/down-sampler (pointwise kernel: one thread = 4 consecutive channels of one pixel; resampling kernel below).
 // FIR taps: outer([1,3,3,1])/64 (down) or /16 (up, gain 4) -- up_or_down_sampling.py:182-258.
 // ------------------------------------------------------------------------------------------------
 struct ApplyArgs {
@@ -318,6 +318,7 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
 }
 
 __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
+  // pointwise form (no resampling): one thread = 4 consecutive channels of one pixel
   int C = a.C0 + a.C1;
   int C4 = C >> 2;
   long long total = (long long)a.B * a.H * a.W * C4;
@@ -333,60 +334,130 @@ __global__ void __launch_bounds__(256) k_apply(ApplyArgs a) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) t[k] = a.tab[(long long)b * C + c + k];
     }
-    float4 out, out2 = make_float4(0.f, 0.f, 0.f, 0.f), rw;
-    if (a.flags & MCVD_F_DOWN) {
-      // out[y,x] = sum_{i,j} k[i]k[j]/64 * in[2y+i-1, 2x+j-1]
-      const float kw[4] = {1.f, 3.f, 3.f, 1.f};
-      out = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float4 v = apply_fetch(a, b, 2 * y + ii - 1, 2 * x + jj - 1, c, t, rw);
-          fma4(out, kw[ii] * kw[jj] * (1.f / 64.f), v);
-          fma4(out2, kw[ii] * kw[jj] * (1.f / 64.f), rw);
-        }
-    } else if (a.flags & MCVD_F_UP) {
-      // even y=2a: (in[a-1] + 3 in[a]) / 4 ; odd y=2a+1: (3 in[a] + in[a+1]) / 4   (per axis)
-      int ya = y >> 1, xa = x >> 1;
-      int y0, y1, x0, x1;
-      float wy0, wy1, wx0, wx1;
-      if (y & 1) { y0 = ya; y1 = ya + 1; wy0 = 3.f; wy1 = 1.f; } else { y0 = ya - 1; y1 = ya; wy0 = 1.f; wy1 = 3.f; }
-      if (x & 1) { x0 = xa; x1 = xa + 1; wx0 = 3.f; wx1 = 1.f; } else { x0 = xa - 1; x1 = xa; wx0 = 1.f; wx1 = 3.f; }
-      out = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v;
-      v = apply_fetch(a, b, y0, x0, c, t, rw); fma4(out, wy0 * wx0 * (1.f / 16.f), v); fma4(out2, wy0 * wx0 * (1.f / 16.f), rw);
-      v = apply_fetch(a, b, y0, x1, c, t, rw); fma4(out, wy0 * wx1 * (1.f / 16.f), v); fma4(out2, wy0 * wx1 * (1.f / 16.f), rw);
-      v = apply_fetch(a, b, y1, x0, c, t, rw); fma4(out, wy1 * wx0 * (1.f / 16.f), v); fma4(out2, wy1 * wx0 * (1.f / 16.f), rw);
-      v = apply_fetch(a, b, y1, x1, c, t, rw); fma4(out, wy1 * wx1 * (1.f / 16.f), v); fma4(out2, wy1 * wx1 * (1.f / 16.f), rw);
-    } else {
-      out = apply_fetch(a, b, y, x, c, t, rw);
-      out2 = rw;
-    }
-    if (a.dst2) *reinterpret_cast<float4*>(a.dst2 + pix * C + c) = out2;
+    float4 rw;
+    float4 out = apply_fetch(a, b, y, x, c, t, rw);
+    if (a.dst2) *reinterpret_cast<float4*>(a.dst2 + pix * C + c) = rw;
     *reinterpret_cast<float4*>(a.dst + pix * C + c) = out;
   }
+}
+
+// Resampling form.  A CTA owns (sample, output tile, 32-channel chunk): it transforms the input tile
+// (+ FIR halo) ONCE into shared memory -- transformed and raw copies -- and every output pixel then
+// takes its 4 (up) or 16 (down) taps from there.  The pointwise form above re-did the transform
+// (two MUFU per element) for every tap; this one reads each input element once from HBM and keeps
+// global accesses in 128-byte rows (8 lanes x float4 per pixel).
+//   up:   16x16 outputs <- 10x10 inputs (8x8 + 1 halo);  even y=2a: (in[a-1] + 3 in[a])/4, odd: (3 in[a] + in[a+1])/4
+//   down: 4x8 outputs   <- 10x18 inputs;                 out[y,x] = sum_ij k_i k_j / 64 * in[2y+i-1, 2x+j-1]
+constexpr int RS_LANES = 8;                 // float4 lanes per pixel = 32 channels per CTA
+template <bool UP>
+struct RsTile {
+  static constexpr int OH = UP ? 16 : 4, OW = UP ? 16 : 8;
+  static constexpr int IH = UP ? 10 : 10, IW = UP ? 10 : 18;
+};
+
+template <bool UP>
+__global__ void __launch_bounds__(256) k_apply_resample(ApplyArgs a, int tiles_x) {
+  using T = RsTile<UP>;
+  extern __shared__ float4 rs_smem[];
+  float4* sT = rs_smem;                                   // [IH*IW][8] transformed
+  float4* sR = rs_smem + T::IH * T::IW * RS_LANES;        // [IH*IW][8] raw (only when dst2)
+  const int C = a.C0 + a.C1;
+  const int b = blockIdx.z;
+  const int ty = blockIdx.x / tiles_x, tx = blockIdx.x % tiles_x;
+  const int lane = threadIdx.x & (RS_LANES - 1);
+  const int c = (blockIdx.y * RS_LANES + lane) * 4;
+  const bool c_ok = c < C;
+  const int iy0 = UP ? ty * (T::OH / 2) - 1 : ty * (T::OH * 2) - 1;
+  const int ix0 = UP ? tx * (T::OW / 2) - 1 : tx * (T::OW * 2) - 1;
+  float4 t[4];
+  if (a.tab && c_ok) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = a.tab[(long long)b * C + c + k];
+  }
+  const bool want_raw = a.dst2 != nullptr;
+#pragma unroll 4
+  for (int px = threadIdx.x >> 3; px < T::IH * T::IW; px += 256 / RS_LANES) {
+    int ly = px / T::IW, lx = px - ly * T::IW;
+    float4 rw = make_float4(0.f, 0.f, 0.f, 0.f), v = rw;
+    if (c_ok) v = apply_fetch(a, b, iy0 + ly, ix0 + lx, c, t, rw);
+    sT[px * RS_LANES + lane] = v;
+    if (want_raw) sR[px * RS_LANES + lane] = rw;
+  }
+  __syncthreads();
+  if (!c_ok) return;
+  for (int op = threadIdx.x >> 3; op < T::OH * T::OW; op += 256 / RS_LANES) {
+    int oy = op / T::OW, ox = op - oy * T::OW;
+    int Y = ty * T::OH + oy, X = tx * T::OW + ox;
+    if (Y >= a.H || X >= a.W) continue;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f), out2 = out;
+    if (UP) {
+      // local rows r0, r0+1 with weights (1,3) for even outputs and (3,1) for odd ones
+      int r0 = (oy >> 1) + (oy & 1), q0 = (ox >> 1) + (ox & 1);
+      float wy0 = (oy & 1) ? 3.f : 1.f, wx0 = (ox & 1) ? 3.f : 1.f;
+      float wy[2] = {wy0, 4.f - wy0}, wx[2] = {wx0, 4.f - wx0};
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          int p = ((r0 + i) * T::IW + q0 + j) * RS_LANES + lane;
+          float w = wy[i] * wx[j] * (1.f / 16.f);
+          fma4(out, w, sT[p]);
+          if (want_raw) fma4(out2, w, sR[p]);
+        }
+    } else {
+      const float kw[4] = {1.f, 3.f, 3.f, 1.f};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          int p = ((2 * oy + i) * T::IW + 2 * ox + j) * RS_LANES + lane;
+          float w = kw[i] * kw[j] * (1.f / 64.f);
+          fma4(out, w, sT[p]);
+          if (want_raw) fma4(out2, w, sR[p]);
+        }
+    }
+    long long pix = ((long long)b * a.H + Y) * a.W + X;
+    if (want_raw) *reinterpret_cast<float4*>(a.dst2 + pix * C + c) = out2;
+    *reinterpret_cast<float4*>(a.dst + pix * C + c) = out;
+  }
+}
+
+template <bool UP>
+static void launch_resample(const ApplyArgs& a, cudaStream_t s) {
+  using T = RsTile<UP>;
+  int C = a.C0 + a.C1;
+  int tiles_x = (a.W + T::OW - 1) / T::OW, tiles_y = (a.H + T::OH - 1) / T::OH;
+  dim3 grid(tiles_x * tiles_y, (C / 4 + RS_LANES - 1) / RS_LANES, a.B);
+  size_t smem = (size_t)T::IH * T::IW * RS_LANES * sizeof(float4) * 2;
+  k_apply_resample<UP><<<grid, 256, smem, s>>>(a, tiles_x);
 }
 
 int launch_apply(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.dst && (op.C1 == 0 || op.src1), "APPLY: null pointer");
   MCVD_CHECK(op.C0 % 4 == 0 && op.C1 % 4 == 0, "APPLY: channels must be multiples of 4 (%d, %d)", op.C0, op.C1);
   MCVD_CHECK(!(op.aux1) || (op.aux2 && op.aux0), "APPLY: SPADE needs gamma, beta and the norm table");
+  MCVD_CHECK(!((op.flags & MCVD_F_DOWN) && (op.flags & MCVD_F_UP)), "APPLY: both UP and DOWN set");
   ApplyArgs a;
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.tab = (const float4*)op.aux0;
   a.gam = (const float*)op.aux1; a.bet = (const float*)op.aux2; a.dst = (float*)op.dst; a.dst2 = (float*)op.dst2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.flags = op.flags;
   a.Hin = op.H; a.Win = op.W;
-  if (op.flags & MCVD_F_DOWN) { a.Hin = op.H * 2; a.Win = op.W * 2; }
-  if (op.flags & MCVD_F_UP) {
+  if (op.B <= 0 || op.H <= 0 || op.W <= 0 || op.C0 + op.C1 <= 0) return 0;
+  if (op.flags & MCVD_F_DOWN) {
+    MCVD_CHECK(op.B <= 65535, "APPLY: batch too large for the resampling grid (%d)", op.B);
+    a.Hin = op.H * 2; a.Win = op.W * 2;
+    launch_resample<false>(a, s);
+  } else if (op.flags & MCVD_F_UP) {
     MCVD_CHECK(op.H % 2 == 0 && op.W % 2 == 0, "APPLY: upsample output must be even");
+    MCVD_CHECK(op.B <= 65535, "APPLY: batch too large for the resampling grid (%d)", op.B);
     a.Hin = op.H / 2; a.Win = op.W / 2;
+    launch_resample<true>(a, s);
+  } else {
+    long long total = (long long)op.B * op.H * op.W * ((op.C0 + op.C1) / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    k_apply<<<(unsigned)blocks, 256, 0, s>>>(a);
   }
-  long long total = (long long)op.B * op.H * op.W * ((op.C0 + op.C1) / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > 148LL * 32) blocks = 148LL * 32;
-  if (blocks < 1) blocks = 1;
-  k_apply<<<(unsigned)blocks, 256, 0, s>>>(a);
   MCVD_CUDA_LAUNCH_CHECK("apply");
   return 0;
 }

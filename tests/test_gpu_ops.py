@@ -167,12 +167,14 @@ def test_groupnorm_table(B, H, C0, C1):
 
 @pytest.mark.parametrize("mode", ["none", "down", "up"])
 @pytest.mark.parametrize("spade", [False, True])
-def test_apply_fir(mode, spade):
-    import sys, os
+@pytest.mark.parametrize("B,Hin,C0,C1", [(2, 16, 32, 16),     # 48 channels: a full and a half 32-channel chunk
+                                         (3, 6, 8, 4),        # tiles larger than the image, odd output size (down -> 3)
+                                         (1, 36, 64, 0)])     # several tiles with a ragged edge, single source
+def test_apply_fir(mode, spade, B, Hin, C0, C1):
     from oracle import mcvd_oracle as O
-    B, Hin, C0, C1 = 2, 16, 32, 16
     C = C0 + C1
-    x0, x1 = rnd(B, Hin, Hin, C0, seed=1), rnd(B, Hin, Hin, C1, seed=2)
+    x0 = rnd(B, Hin, Hin, C0, seed=1)
+    x1 = rnd(B, Hin, Hin, C1, seed=2) if C1 else torch.zeros(B, Hin, Hin, 0)
     tab = make_table(B, C)
     gam, bet = rnd(B, Hin, Hin, C, seed=8) * 0.2, rnd(B, Hin, Hin, C, seed=9) * 0.2
     x = torch.cat([x0, x1], 3)
@@ -190,7 +192,7 @@ def test_apply_fir(mode, spade):
     elif mode == "up":
         n, raw, H, fl = O.fir_upsample(n), O.fir_upsample(raw), Hin * 2, lib.F_UP
     d = lambda t_: t_.to(DEV).contiguous()
-    x0d, x1d, td, gd, bd = d(x0), d(x1), d(tab), d(gam), d(bet)
+    x0d, x1d, td, gd, bd = d(x0), (d(x1) if C1 else None), d(tab), d(gam), d(bet)
     o1 = torch.zeros(B, H, H, C, device=DEV)
     o2 = torch.zeros(B, H, H, C, device=DEV)
     o3 = torch.zeros(B, H, H, C, device=DEV)
