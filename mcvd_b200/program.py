@@ -27,7 +27,14 @@ from . import arch, lib
 from .lib import McvdOp
 
 INV_SQRT2 = float(1.0 / math.sqrt(2.0))
-GN_PPC = 64          # pixels per chunk in the GroupNorm partial pass
+GN_PPC = 64          # pixels per chunk in the GroupNorm partial pass at 32x32 and above
+
+
+def gn_chunks(hw: int) -> int:
+    """Chunks (CTAs per sample) of the GroupNorm partial pass: 64-pixel chunks on large maps, but never fewer
+    than 16 chunks (8-pixel floor) so the 8x8 / 16x16 levels still put >= 512 CTAs on the 148 SMs at B = 64
+    (one chunk per sample left them latency-bound at ~22 us per launch)."""
+    return max(1, min(hw // 8, max(hw // GN_PPC, 16)))
 
 
 class Src:
@@ -310,7 +317,7 @@ class Engine:
         def norm_table(ops, src: Src, H: int, eps: float, film_off=None, affine=None):
             C = src.C
             cg = C // arch.num_groups(C)
-            nchunk = max(1, (H * H) // GN_PPC)
+            nchunk = gn_chunks(H * H)
             tab = f32(B, C, 4)
             p0 = partials_of(ops, src.t0, src.c0, H, nchunk)
             p1 = partials_of(ops, src.t1, src.c1, H, nchunk) if src.t1 is not None else None
