@@ -356,7 +356,7 @@ def roofline(net, P, B, cfg, pk, pk_src):
             ms = evs[i].elapsed_time(evs[i + 1])
             k = tot.setdefault(op.kind, [0.0, 0])
             k[0] += ms
-            k[1] += 1
+            k[1] += 2 if op.kind == lib.OP_ATTENTION_UMMA else 1   # pre-split + attention kernels
             if op.kind == lib.OP_CONV_UMMA and rep == 0:
                 flops_umma += 2.0 * op.B * op.H * op.W * (op.C0 + op.C1) * op.Cout * op.i0 * op.i0
     names = {v: k for k, v in vars(lib).items() if k.startswith("OP_")}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCVD_ABI_VERSION 2
+#define MCVD_ABI_VERSION 3
 
 /* ---- op kinds ------------------------------------------------------------------------------- */
 enum {
@@ -104,8 +104,11 @@ enum {
   /* dst[i] = src0[i] (i0 floats) -- device-to-device copy inside a program. */
   MCVD_OP_COPY = 14,
   /* MCVD_OP_ATTENTION on the tensor cores (tcgen05, fp16 hi/lo split, flash-style online softmax with
-   * S and the per-tile P.V product in TMEM); same fields.  Head dim in {32,48,64,96,128}, H*W a
-   * multiple of the key tile (128, or 64 for head dim 128).  See mcvd_b200/csrc/attention_umma.cu. */
+   * S and the per-tile P.V product in TMEM); same fields plus dst2 = device scratch of at least
+   * mcvd_attention_scratch_bytes(B, H*W, C0) bytes (16-byte aligned): a first kernel splits q, k, v into
+   * fp16 hi/lo operand images there, the attention kernel streams them in with cp.async.bulk (2 launches).
+   * Head dim in {32,48,64,96,128}, H*W a multiple of the key tile (128, or 64 for head dim 128; 64 when
+   * H*W = 64).  See mcvd_b200/csrc/attention_umma.cu. */
   MCVD_OP_ATTENTION_UMMA = 15,
   MCVD_OP__COUNT
 };
@@ -173,6 +176,8 @@ long long mcvd_umma_pack_weights(const float* w_taps, int taps, int Cin, int Cou
 /* Channels per K-block (32, 16, or 0 = unsupported) the tensor-core conv uses for sources with C0 / C1
  * channels; the packed weights must be produced with the same value. */
 int mcvd_umma_kblock(int C0, int C1);
+/* Bytes of dst2 scratch one MCVD_OP_ATTENTION_UMMA op with batch B, T = H*W tokens and C channels needs. */
+long long mcvd_attention_scratch_bytes(int B, int T, int C);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,10 @@ static int validate_one(const McvdOp& op, int idx) {
         set_error("op %d ATTENTION: heads %d x dim %d != %d", idx, op.i0, op.i1, op.C0);
         return -1;
       }
+      if (op.kind == MCVD_OP_ATTENTION_UMMA && (!op.dst2 || (reinterpret_cast<uintptr_t>(op.dst2) & 15))) {
+        set_error("op %d ATTENTION_UMMA: dst2 (operand-image scratch) is null or not 16-byte aligned", idx);
+        return -1;
+      }
       break;
     default: break;
   }
@@ -130,7 +134,9 @@ int mcvd_validate_program(const McvdOp* ops, int n) {
 
 int mcvd_count_launches(const McvdOp* ops, int n) {
   if (!ops || n < 0) return -1;
-  return n;  // every op kind is exactly one kernel launch
+  int total = 0;
+  for (int i = 0; i < n; ++i) total += (ops[i].kind == MCVD_OP_ATTENTION_UMMA) ? 2 : 1;   // pre-split + attention
+  return total;
 }
 
 int mcvd_run_program(const McvdOp* ops, int n, void* stream) {

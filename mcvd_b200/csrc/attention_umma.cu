@@ -16,8 +16,14 @@
 // Operand layouts (canonical K-major, no swizzle): [k-chunk of 8 halfs][row][16 B], LBO = rows*16,
 // SBO = 128.   V is staged transposed (rows = channels, k = keys) so it is K-major too.
 //
-// Warps: 0-3 softmax / output (thread r <-> query row r <-> TMEM lane r), 4-7 K/V stagers,
-//        8 TMEM allocation + MMA issue.
+// Two launches per op:
+//   k_attn_presplit  converts q, k, v ONCE into fp16 hi/lo "operand images" in a scratch buffer, one image per
+//                    (sample, head, tile), byte-for-byte what the MMA wants in shared memory.  (Converting
+//                    inside the attention kernel re-did the K/V tiles for each of the T/128 query tiles
+//                    and left it bound by the latency of the staging loops: 400 us at 32x32 in cfg2.)
+//   k_attention_umma one thread streams the images in with cp.async.bulk (mbarrier complete_tx).
+// Warps: 0-3 softmax / output (thread r <-> query row r <-> TMEM lane r), 4 image loader,
+//        5 TMEM allocation + MMA issue.
 #include "mcvd_common.cuh"
 #include "umma_ptx.cuh"
 
@@ -28,12 +34,15 @@ namespace {
 using namespace ptx;
 
 constexpr int QT = 128;
-constexpr int ATT_THREADS = 288;
+constexpr int ATT_THREADS = 192;
+constexpr int SPLIT_THREADS = 256;
 
 struct AttnArgs {
   const float* qkv;
   float* out;
-  int T, C, KT, nkt, tmem_cols;
+  uint8_t* img;                 // operand images: [Q tiles | K tiles | V tiles], see image_offsets()
+  long long k_off, v_off;       // byte offsets of the K and V image arrays
+  int T, C, KT, nkt, nqt, tmem_cols;
   float scale;
 };
 
@@ -82,6 +91,73 @@ __device__ __forceinline__ void stage_rows(uint8_t* hi, uint8_t* lo, const float
   }
 }
 
+// V^T image: rows = channels, k = keys.  unit = (key chunk kc of 8 keys, 4 channels): 8 x LDG.128 (one per
+// key, 4 channels each), transposed in registers into 4 rows of 8 keys; 2 units (16 loads) in flight.
+template <int D>
+__device__ __forceinline__ void stage_v(uint8_t* vh, uint8_t* vl, const float* vsrc, long long stride, int KT, int tid,
+                                        int nthreads) {
+  constexpr int C4 = D / 4;
+  const int vunits = (KT / 8) * C4;
+  for (int u0 = tid; u0 < vunits; u0 += 2 * nthreads) {
+    float4 ld[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int u = u0 + i * nthreads;
+      const int kc = u / C4, c4 = u - kc * C4;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        ld[i][e] = (u < vunits) ? __ldg(reinterpret_cast<const float4*>(vsrc + (long long)(kc * 8 + e) * stride) + c4)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int u = u0 + i * nthreads;
+      if (u < vunits) {
+        const int kc = u / C4, c4 = u - kc * C4;
+        const float r0[8] = {ld[i][0].x, ld[i][1].x, ld[i][2].x, ld[i][3].x, ld[i][4].x, ld[i][5].x, ld[i][6].x, ld[i][7].x};
+        const float r1[8] = {ld[i][0].y, ld[i][1].y, ld[i][2].y, ld[i][3].y, ld[i][4].y, ld[i][5].y, ld[i][6].y, ld[i][7].y};
+        const float r2[8] = {ld[i][0].z, ld[i][1].z, ld[i][2].z, ld[i][3].z, ld[i][4].z, ld[i][5].z, ld[i][6].z, ld[i][7].z};
+        const float r3[8] = {ld[i][0].w, ld[i][1].w, ld[i][2].w, ld[i][3].w, ld[i][4].w, ld[i][5].w, ld[i][6].w, ld[i][7].w};
+        uint4 hv, lv;
+        const size_t off = ((size_t)kc * D + c4 * 4) * 16;
+        split8(r0, hv, lv); *reinterpret_cast<uint4*>(vh + off) = hv;      *reinterpret_cast<uint4*>(vl + off) = lv;
+        split8(r1, hv, lv); *reinterpret_cast<uint4*>(vh + off + 16) = hv; *reinterpret_cast<uint4*>(vl + off + 16) = lv;
+        split8(r2, hv, lv); *reinterpret_cast<uint4*>(vh + off + 32) = hv; *reinterpret_cast<uint4*>(vl + off + 32) = lv;
+        split8(r3, hv, lv); *reinterpret_cast<uint4*>(vh + off + 48) = hv; *reinterpret_cast<uint4*>(vl + off + 48) = lv;
+      }
+    }
+  }
+}
+
+// image sizes in bytes (hi plane + lo plane)
+template <int D> __host__ __device__ constexpr long long q_image_bytes() { return 2LL * (D / 8) * QT * 16; }
+template <int D> __host__ __device__ inline long long kv_image_bytes(int KT) { return 2LL * (D / 8) * KT * 16; }
+
+// Pre-pass: grid (nqt + 2 nkt, heads, B); block x builds one Q, K or V image of (sample, head).
+template <int D>
+__global__ void __launch_bounds__(SPLIT_THREADS) k_attn_presplit(const AttnArgs a) {
+  const int x = blockIdx.x, h = blockIdx.y, b = blockIdx.z, heads = gridDim.y;
+  const int C3 = 3 * a.C, KT = a.KT;
+  const float* base = a.qkv + (long long)b * a.T * C3 + h * D;
+  const long long bh = (long long)b * heads + h;
+  if (x < a.nqt) {
+    uint8_t* dst = a.img + (bh * a.nqt + x) * q_image_bytes<D>();
+    const int q0 = x * QT;
+    stage_rows<D>(dst, dst + q_image_bytes<D>() / 2, base + (long long)q0 * C3, C3, QT, min(QT, a.T - q0), threadIdx.x,
+                  SPLIT_THREADS);
+  } else if (x < a.nqt + a.nkt) {
+    const int kt = x - a.nqt;
+    uint8_t* dst = a.img + a.k_off + (bh * a.nkt + kt) * kv_image_bytes<D>(KT);
+    stage_rows<D>(dst, dst + kv_image_bytes<D>(KT) / 2, base + a.C + (long long)kt * KT * C3, C3, KT, KT, threadIdx.x,
+                  SPLIT_THREADS);
+  } else {
+    const int kt = x - a.nqt - a.nkt;
+    uint8_t* dst = a.img + a.v_off + (bh * a.nkt + kt) * kv_image_bytes<D>(KT);
+    stage_v<D>(dst, dst + kv_image_bytes<D>(KT) / 2, base + 2 * a.C + (long long)kt * KT * C3, C3, KT, threadIdx.x,
+               SPLIT_THREADS);
+  }
+}
+
 // 64 consecutive TMEM columns of this thread's lane -> registers (one wait)
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t r[64]) {
   tmem_ld16(taddr, r);
@@ -108,17 +184,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
-  const int C3 = 3 * a.C;
-  const float* base = a.qkv + (long long)b * a.T * C3 + h * D;   // q channels of this head, token 0
+  const long long bh = (long long)b * gridDim.y + h;
 
   if (tid == 0) {
-    mbar_init(K_FULL, 128); mbar_init(V_FULL, 128); mbar_init(P_FULL, 128);
+    mbar_init(K_FULL, 1); mbar_init(V_FULL, 1); mbar_init(P_FULL, 128);
     mbar_init(S_FULL, 1); mbar_init(O_FULL, 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
-  if (tid < 256) stage_rows<D>(qh, ql, base + (long long)q0 * C3, C3, QT, min(QT, a.T - q0), tid, 256);
-  fence_proxy_async();
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -193,55 +266,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       for (int c = 0; c < D; c += 4)
         *reinterpret_cast<float4*>(op + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
     }
-  } else if (warp < 8) {
-    // ================= K / V stagers =================
-    const int st = tid - 128;
-    for (int j = 0; j < a.nkt; ++j) {
-      const int k0 = j * KT;
-      if (j > 0) mbar_wait(S_FULL, (j - 1) & 1);            // S_{j-1} done: K buffer free
-      stage_rows<D>(kh, kl, base + a.C + (long long)k0 * C3, C3, KT, KT, st, 128);
-      fence_proxy_async();
-      mbar_arrive(K_FULL);
-      if (j > 0) mbar_wait(O_FULL, (j - 1) & 1);            // PV_{j-1} done: V buffer free
-      // V^T: rows = channels, k = keys.  unit = (key chunk kc of 8 keys, 4 channels): 8 x LDG.128 (one per
-      // key, 4 channels each), transposed in registers into 4 rows of 8 keys; 2 units (16 loads) in flight.
-      const float* vsrc = base + 2 * a.C + (long long)k0 * C3;
-      constexpr int C4 = D / 4;
-      const int vunits = (KT / 8) * C4;
-      for (int u0 = st; u0 < vunits; u0 += 256) {
-        float4 ld[2][8];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = u0 + i * 128;
-          const int kc = u / C4, c4 = u - kc * C4;
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            ld[i][e] = (u < vunits) ? __ldg(reinterpret_cast<const float4*>(vsrc + (long long)(kc * 8 + e) * C3) + c4)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = u0 + i * 128;
-          if (u < vunits) {
-            const int kc = u / C4, c4 = u - kc * C4;
-            const float r0[8] = {ld[i][0].x, ld[i][1].x, ld[i][2].x, ld[i][3].x, ld[i][4].x, ld[i][5].x, ld[i][6].x, ld[i][7].x};
-            const float r1[8] = {ld[i][0].y, ld[i][1].y, ld[i][2].y, ld[i][3].y, ld[i][4].y, ld[i][5].y, ld[i][6].y, ld[i][7].y};
-            const float r2[8] = {ld[i][0].z, ld[i][1].z, ld[i][2].z, ld[i][3].z, ld[i][4].z, ld[i][5].z, ld[i][6].z, ld[i][7].z};
-            const float r3[8] = {ld[i][0].w, ld[i][1].w, ld[i][2].w, ld[i][3].w, ld[i][4].w, ld[i][5].w, ld[i][6].w, ld[i][7].w};
-            uint4 hv, lv;
-            const size_t off = ((size_t)kc * D + c4 * 4) * 16;
-            split8(r0, hv, lv); *reinterpret_cast<uint4*>(vh + off) = hv;      *reinterpret_cast<uint4*>(vl + off) = lv;
-            split8(r1, hv, lv); *reinterpret_cast<uint4*>(vh + off + 16) = hv; *reinterpret_cast<uint4*>(vl + off + 16) = lv;
-            split8(r2, hv, lv); *reinterpret_cast<uint4*>(vh + off + 32) = hv; *reinterpret_cast<uint4*>(vl + off + 32) = lv;
-            split8(r3, hv, lv); *reinterpret_cast<uint4*>(vh + off + 48) = hv; *reinterpret_cast<uint4*>(vl + off + 48) = lv;
-          }
-        }
+  } else if (warp == 4) {
+    // ================= image loader: one thread, cp.async.bulk global -> smem =================
+    if (elect_one()) {
+      const uint32_t qbytes = (uint32_t)q_image_bytes<D>(), kvbytes = (uint32_t)kv_image_bytes<D>(KT);
+      const uint8_t* qimg = a.img + (bh * a.nqt + blockIdx.x) * q_image_bytes<D>();
+      const uint8_t* kimg = a.img + a.k_off + bh * a.nkt * kv_image_bytes<D>(KT);
+      const uint8_t* vimg = a.img + a.v_off + bh * a.nkt * kv_image_bytes<D>(KT);
+      for (int j = 0; j < a.nkt; ++j) {
+        if (j > 0) mbar_wait(S_FULL, (j - 1) & 1);          // S_{j-1} done: K buffer free
+        // the Q image rides on the first K phase (q | k buffers are adjacent but filled by two copies)
+        mbar_arrive_expect_tx(K_FULL, kvbytes + (j == 0 ? qbytes : 0u));
+        if (j == 0) bulk_g2s(smem_u32(qh), qimg, qbytes, K_FULL);
+        bulk_g2s(smem_u32(kh), kimg + (long long)j * kvbytes, kvbytes, K_FULL);
+        if (j > 0) mbar_wait(O_FULL, (j - 1) & 1);          // PV_{j-1} done: V buffer free
+        mbar_arrive_expect_tx(V_FULL, kvbytes);
+        bulk_g2s(smem_u32(vh), vimg + (long long)j * kvbytes, kvbytes, V_FULL);
       }
-      fence_proxy_async();
-      mbar_arrive(V_FULL);
     }
   } else if (elect_one()) {
-    // ================= MMA issuer (one elected lane of warp 8) =================
+    // ================= MMA issuer (one elected lane of warp 5) =================
     const uint32_t idesc_s = make_idesc_f16(QT, KT), idesc_o = make_idesc_f16(QT, D);
     const uint32_t q_lbo = QT * 16, k_lbo = (uint32_t)KT * 16, v_lbo = D * 16, p_lbo = QT * 16;
     const uint32_t sqh = smem_u32(qh), sql = smem_u32(ql), skh = smem_u32(kh), skl = smem_u32(kl);
@@ -274,7 +318,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
   }
 
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
@@ -287,23 +331,41 @@ int launch_d(const McvdOp& op, cudaStream_t s) {
   a.T = op.H * op.W; a.C = op.C0; a.scale = op.f0;
   a.KT = (D <= 96) ? 128 : 64;
   if (a.T < a.KT) a.KT = a.T;
-  MCVD_CHECK(a.KT % 16 == 0 && a.KT >= 16 && a.T % a.KT == 0, "ATTENTION_UMMA: %d tokens not tileable", a.T);
+  // the softmax warps read S in 64-column passes
+  MCVD_CHECK(a.KT % 64 == 0 && a.T % a.KT == 0, "ATTENTION_UMMA: %d tokens not tileable (need a multiple of 64)", a.T);
   a.nkt = a.T / a.KT;
   int cols = a.KT + D, p2 = 32;
   while (p2 < cols) p2 <<= 1;
   a.tmem_cols = p2;
+  a.nqt = cdiv(a.T, QT);
+  a.img = (uint8_t*)op.dst2;
+  const long long bh = (long long)op.B * op.i0;
+  a.k_off = bh * a.nqt * q_image_bytes<D>();
+  a.v_off = a.k_off + bh * a.nkt * kv_image_bytes<D>(a.KT);
+  MCVD_CHECK(op.dst2, "ATTENTION_UMMA: dst2 (operand-image scratch, mcvd_attention_scratch_bytes) is NULL");
+  MCVD_CHECK((reinterpret_cast<uintptr_t>(op.dst2) & 15) == 0, "ATTENTION_UMMA: scratch must be 16-byte aligned");
   const size_t smem = 2 * ((size_t)(D / 8) * QT * 16 + (size_t)(D / 8) * a.KT * 16 + (size_t)(a.KT / 8) * D * 16 +
                            (size_t)(a.KT / 8) * QT * 16) + 64;
   MCVD_CHECK(smem <= 227 * 1024, "ATTENTION_UMMA: %zu B of shared memory", smem);
   cudaError_t e = cudaFuncSetAttribute(k_attention_umma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MCVD_CHECK(e == cudaSuccess, "ATTENTION_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  dim3 grid(cdiv(a.T, QT), op.i0, op.B);
+  dim3 sgrid(a.nqt + 2 * a.nkt, op.i0, op.B);
+  k_attn_presplit<D><<<sgrid, SPLIT_THREADS, 0, s>>>(a);
+  MCVD_CUDA_LAUNCH_CHECK("attention presplit");
+  dim3 grid(a.nqt, op.i0, op.B);
   k_attention_umma<D><<<grid, ATT_THREADS, smem, s>>>(a);
   MCVD_CUDA_LAUNCH_CHECK("attention_umma");
   return 0;
 }
 
 }  // namespace
+
+// bytes of operand-image scratch an ATTENTION_UMMA op needs: Q padded to whole 128-row tiles, K and V
+// exactly T rows; fp16 hi + lo = 4 bytes per element
+long long attention_umma_scratch_bytes(int B, int T, int C) {
+  if (B <= 0 || T <= 0 || C <= 0) return 0;
+  return 4LL * B * C * ((long long)cdiv(T, QT) * QT + 2LL * T);
+}
 
 int launch_attention_umma(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.dst, "ATTENTION_UMMA: null pointer");
@@ -321,3 +383,7 @@ int launch_attention_umma(const McvdOp& op, cudaStream_t s) {
 }
 
 }  // namespace mcvd
+
+extern "C" long long mcvd_attention_scratch_bytes(int B, int T, int C) {
+  return mcvd::attention_umma_scratch_bytes(B, T, C);
+}

@@ -36,10 +36,11 @@ F_FILM = 1 << 4
 F_CLIP = 1 << 5
 F_PHILOX = 1 << 6
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = ["mcvd_abi_version", "mcvd_sizeof_op", "mcvd_last_error", "mcvd_device_arch", "mcvd_run_program",
-           "mcvd_validate_program", "mcvd_count_launches", "mcvd_umma_pack_weights", "mcvd_umma_kblock"]
+           "mcvd_validate_program", "mcvd_count_launches", "mcvd_umma_pack_weights", "mcvd_umma_kblock",
+           "mcvd_attention_scratch_bytes"]
 
 
 class McvdOp(C.Structure):
@@ -98,6 +99,8 @@ def load():
                                                C.c_int, C.c_void_p]
         lib.mcvd_umma_kblock.restype = C.c_int
         lib.mcvd_umma_kblock.argtypes = [C.c_int, C.c_int]
+        lib.mcvd_attention_scratch_bytes.restype = C.c_longlong
+        lib.mcvd_attention_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         if lib.mcvd_abi_version() != ABI_VERSION:
             raise RuntimeError("mcvd_b200: ABI version mismatch between the Python binding and the library")
         if lib.mcvd_sizeof_op() != C.sizeof(McvdOp):
@@ -130,3 +133,8 @@ def validate_program(arr, n):
 
 def umma_kblock(c0: int, c1: int) -> int:
     return int(load().mcvd_umma_kblock(c0, c1))
+
+
+def attention_scratch_bytes(B: int, T: int, C: int) -> int:
+    """bytes of ``dst2`` scratch an OP_ATTENTION_UMMA op needs (fp16 hi/lo operand images of q, k, v)"""
+    return int(load().mcvd_attention_scratch_bytes(B, T, C))

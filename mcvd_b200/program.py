@@ -75,6 +75,19 @@ class Program:
         self.film_fin_idx: List[int] = []    # GN_FINALIZE ops that read the FiLM table
         self.uniform_t = False
 
+    @staticmethod
+    def count_launches(ops) -> int:
+        """kernel launches of an op list (the tensor-core attention op is a pre-split + the attention kernel)"""
+        return sum(2 if o.kind == lib.OP_ATTENTION_UMMA else 1 for o in ops)
+
+    @property
+    def cond_launches(self) -> int:
+        return self.count_launches(self.cond_ops)
+
+    @property
+    def step_launches(self) -> int:
+        return self.count_launches(self.step_ops)
+
 
 class Engine:
     def __init__(self, module, _test_backend=None):
@@ -430,6 +443,8 @@ class Engine:
             return conv(step, pre + "Conv_1", Src(h, Cout), H, Cout, 3, pre + "Conv_1.weight", pre + "Conv_1.bias",
                         residual=res, scale=INV_SQRT2, tab=tab1, act_in=True, shortcut=shortcut)
 
+        attn_scratch = [None]
+
         def attnblock(ms: arch.ModSpec, x: torch.Tensor) -> torch.Tensor:
             pre = f"unet.all_modules.{ms.idx}."
             H, C = ms.res, ms.in_ch
@@ -442,9 +457,17 @@ class Engine:
             d = C // ms.heads
             T = H * H
             kt = min(T, 128 if d <= 96 else 64)
-            use_tc = self.attn_mode == "umma" and d in (32, 48, 64, 96, 128) and T % kt == 0 and kt % 16 == 0
-            emit(step, lib.OP_ATTENTION_UMMA if use_tc else lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d,
-                 f0=float(int(d) ** (-0.5)), src0=qkv, dst=att)
+            use_tc = self.attn_mode == "umma" and d in (32, 48, 64, 96, 128) and T % kt == 0 and kt % 64 == 0
+            if use_tc:
+                # q/k/v operand images (fp16 hi/lo); one scratch serves every attention layer (stream order)
+                need = lib.attention_scratch_bytes(B, T, C)
+                if attn_scratch[0] is None or attn_scratch[0].numel() < need:
+                    attn_scratch[0] = keep(torch.empty(need, device=dev, dtype=torch.uint8))
+                emit(step, lib.OP_ATTENTION_UMMA, H=H, W=H, C0=C, i0=ms.heads, i1=d, f0=float(int(d) ** (-0.5)),
+                     src0=qkv, dst=att, dst2=attn_scratch[0])
+            else:
+                emit(step, lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d, f0=float(int(d) ** (-0.5)),
+                     src0=qkv, dst=att)
             return conv(step, pre + "NIN_3", Src(att, C), H, C, 1, pre + "NIN_3.W", pre + "NIN_3.b", residual=x,
                         scale=INV_SQRT2, nin=True)
 
@@ -606,5 +629,5 @@ class Engine:
             self.run_cond(P)
             self.run_step(P)
             self._run(P.out_arr, 1)
-            self.launches_last_forward = len(P.cond_ops) + len(P.step_ops) + 1
+            self.launches_last_forward = P.cond_launches + P.step_launches + 1
             return P.out.clone()

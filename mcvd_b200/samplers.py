@@ -63,7 +63,7 @@ class _Loop:
             raise RuntimeError("mcvd_b200: cond is required by this network")
         self.eng.set_inputs(self.P, x=x_mod.float(), cond=None if cond is None else cond.float())
         self.eng.run_cond(self.P)
-        self.launches += len(self.P.cond_ops)
+        self.launches += self.P.cond_launches
         self.u = self.P.update_arr[0]
 
     def close(self):
@@ -73,7 +73,7 @@ class _Loop:
         """eps = net(x_state, t, cond) into P.eps_nhwc (x_state = P.x_in)."""
         self.eng.set_inputs(self.P, t=t)
         self.eng.run_step_graphed(self.P)
-        self.launches += len(self.P.step_ops)
+        self.launches += self.P.step_launches
 
     def update(self, k0, k1, ca, cb, cc, sigma, clip, noise=None, philox=None, step=0):
         u = self.u

@@ -1,5 +1,6 @@
 """Per-kernel parity on the B200, through the C-ABI: every op kind against a torch fp32 CPU evaluation
 of the same op (tests/op_interpreter.py semantics == include/mcvd_b200.h)."""
+import ctypes
 import math
 
 import pytest
@@ -218,8 +219,14 @@ def test_attention(B, H, heads, d, kind):
     ref = torch.einsum("bhts,bshd->bthd", torch.softmax(s, -1), v.double()).reshape(B, T, C).float()
     qd = qkv.to(DEV)
     out = torch.zeros(B, T, C, device=DEV)
-    run([mk(lib.OP_ATTENTION if kind == "simt" else lib.OP_ATTENTION_UMMA, B, H=H, W=H, C0=C, i0=heads, i1=d, f0=scale,
-            src0=qd, dst=out)])
+    if kind == "simt":
+        run([mk(lib.OP_ATTENTION, B, H=H, W=H, C0=C, i0=heads, i1=d, f0=scale, src0=qd, dst=out)])
+    else:
+        scratch = torch.empty(lib.attention_scratch_bytes(B, T, C), dtype=torch.uint8, device=DEV)
+        assert scratch.numel() == 4 * B * C * (-(-T // 128) * 128 + 2 * T)
+        op = mk(lib.OP_ATTENTION_UMMA, B, H=H, W=H, C0=C, i0=heads, i1=d, f0=scale, src0=qd, dst=out, dst2=scratch)
+        assert lib.load().mcvd_count_launches(ctypes.byref(op), 1) == 2        # pre-split + attention
+        run([op])
     assert (out.cpu() - ref).abs().max().item() < 2e-5
 
 
