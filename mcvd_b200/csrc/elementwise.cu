@@ -103,6 +103,33 @@ __global__ void __launch_bounds__(128) k_linear(const float* __restrict__ src, c
   int j = blockIdx.x * 4 + warp;
   if (j >= N) return;
   const float* wr = w + (long long)j * K;
+  if (B == 1) {
+    // uniform-timestep sampling: one row (the per-step FiLM projection is a 33k x 384 GEMV) -- stream the
+    // weight row with 16-byte loads when it is aligned, one shuffle tree
+    float acc = 0.f;
+    if ((K & 3) == 0) {
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+        float4 xv = *reinterpret_cast<const float4*>(src + k);
+        if (flags & MCVD_F_ACT_IN) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+        acc = fmaf(wv.x, xv.x, acc); acc = fmaf(wv.y, xv.y, acc); acc = fmaf(wv.z, xv.z, acc); acc = fmaf(wv.w, xv.w, acc);
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        float xv = src[k];
+        if (flags & MCVD_F_ACT_IN) xv = silu_f(xv);
+        acc = fmaf(wr[k], xv, acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      acc += bias ? bias[j] : 0.f;
+      if (flags & MCVD_F_ACT_OUT) acc = silu_f(acc);
+      dst[j] = acc;
+    }
+    return;
+  }
   for (int b0 = 0; b0 < B; b0 += LIN_BT) {
     float acc[LIN_BT];
 #pragma unroll
@@ -120,10 +147,11 @@ __global__ void __launch_bounds__(128) k_linear(const float* __restrict__ src, c
     }
 #pragma unroll
     for (int i = 0; i < LIN_BT; ++i) {
+      if (b0 + i >= B) break;                              // uniform across the warp
       float v = acc[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && b0 + i < B) {
+      if (lane == 0) {
         v += bias ? bias[j] : 0.f;
         if (flags & MCVD_F_ACT_OUT) v = silu_f(v);
         dst[(long long)(b0 + i) * N + j] = v;

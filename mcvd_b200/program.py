@@ -27,14 +27,15 @@ from . import arch, lib
 from .lib import McvdOp
 
 INV_SQRT2 = float(1.0 / math.sqrt(2.0))
-GN_PPC = 64          # pixels per chunk in the GroupNorm partial pass at 32x32 and above
+GN_PPC = 64          # pixels per chunk in the GroupNorm partial pass on large maps
+GN_MIN_CHUNKS = 32   # ... but at least this many chunks per sample (8-pixel floor)
 
 
 def gn_chunks(hw: int) -> int:
     """Chunks (CTAs per sample) of the GroupNorm partial pass: 64-pixel chunks on large maps, but never fewer
-    than 16 chunks (8-pixel floor) so the 8x8 / 16x16 levels still put >= 512 CTAs on the 148 SMs at B = 64
+    than GN_MIN_CHUNKS chunks (8-pixel floor) so the 8x8 .. 32x32 levels still put >= 512 CTAs on the 148 SMs at B = 64
     (one chunk per sample left them latency-bound at ~22 us per launch)."""
-    return max(1, min(hw // 8, max(hw // GN_PPC, 16)))
+    return max(1, min(hw // 8, max(hw // GN_PPC, GN_MIN_CHUNKS)))
 
 
 class Src:

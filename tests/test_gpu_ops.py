@@ -245,6 +245,14 @@ def test_linear_embed_layout_update():
          mk(lib.OP_LINEAR, B, C0=nf, Cout=48, src0=e, w=wd, bias=bd, dst=y, flags=lib.F_ACT_OUT)])
     assert (e.cpu() - e_ref).abs().max().item() < 2e-6
     assert (y.cpu() - y_ref).abs().max().item() < 1e-5
+    # single-row GEMV path (uniform-timestep sampling: the FiLM projection of one temb row), K % 4 == 0 and not
+    for K in (384, 30):
+        xs, ws, bs = rnd(1, K, seed=5), rnd(77, K, seed=6) * 0.1, rnd(77, seed=7)
+        ys_ref = F.linear(F.silu(xs), ws, bs)
+        ys = torch.zeros(1, 77, device=DEV)
+        run([mk(lib.OP_LINEAR, 1, C0=K, Cout=77, src0=xs.to(DEV), w=ws.to(DEV).contiguous(), bias=bs.to(DEV), dst=ys,
+                flags=lib.F_ACT_IN)])
+        assert (ys.cpu() - ys_ref).abs().max().item() < 1e-5
     # layout round trip + diffusion update
     B, C, S = 2, 5, 16
     x, c = rnd(B, C, S, S, seed=3), rnd(B, 3, S, S, seed=4)
