@@ -22,8 +22,11 @@
 //                    inside the attention kernel re-did the K/V tiles for each of the T/128 query tiles
 //                    and left it bound by the latency of the staging loops: 400 us at 32x32 in cfg2.)
 //   k_attention_umma one thread streams the images in with cp.async.bulk (mbarrier complete_tx).
-// Warps: 0-3 softmax / output (thread r <-> query row r <-> TMEM lane r), 4 image loader,
-//        5 TMEM allocation + MMA issue.
+// Warps: 0-7 softmax / output: query row r <-> TMEM lane r is shared by TWO threads (warp w and w+4 both own
+//        lane group w%4, the only TMEM lanes either may touch); each takes half of the key columns of S and half of
+//        the channels of O, and they meet through shared memory for the row maximum and the final row sum.  (One
+//        thread per row left a single warp per SMSP running a dependent MUFU / tcgen05.ld chain: 29 % issue slots.)
+//        8 image loader, 9 TMEM allocation + MMA issue.
 #include "mcvd_common.cuh"
 #include "umma_ptx.cuh"
 
@@ -34,7 +37,8 @@ namespace {
 using namespace ptx;
 
 constexpr int QT = 128;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;       // 8 softmax warps + image loader + MMA issuer
+constexpr int SOFTMAX_THREADS = 256;
 constexpr int SPLIT_THREADS = 256;
 
 struct AttnArgs {
@@ -181,50 +185,68 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
   const uint32_t bar0 = smem_u32(bars);
   const uint32_t K_FULL = bar0, V_FULL = bar0 + 8, P_FULL = bar0 + 16, S_FULL = bar0 + 24, O_FULL = bar0 + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  float* xmax = reinterpret_cast<float*>(bars + 8);        // [tile parity][half][QT] partial row maxima
+  float* xsum = xmax + 4 * QT;                             // [half][QT] partial row sums
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * QT, h = blockIdx.y, b = blockIdx.z;
   const long long bh = (long long)b * gridDim.y + h;
 
   if (tid == 0) {
-    mbar_init(K_FULL, 1); mbar_init(V_FULL, 1); mbar_init(P_FULL, 128);
+    mbar_init(K_FULL, 1); mbar_init(V_FULL, 1); mbar_init(P_FULL, SOFTMAX_THREADS);
     mbar_init(S_FULL, 1); mbar_init(O_FULL, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tO = tmem_base + (uint32_t)KT;
 
-  if (warp < 4) {
-    // ================= softmax + output accumulation: thread r owns query row r =================
-    const int r = tid;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-    float o[D];
+  if (warp < 8) {
+    // ================= softmax + output accumulation: two threads per query row =================
+    const int lg = warp & 3, hf = warp >> 2;                // TMEM lane group, column / channel half
+    const int r = lg * 32 + (tid & 31);
+    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+    constexpr int D0 = ((D / 2 + 15) / 16) * 16;            // channels of half 0 (half 1 takes the rest)
+    const int oc0 = hf ? D0 : 0, n_o = hf ? D - D0 : D0;
+    const int half_cols = KT / 2;                           // 64 or 32 key columns per thread and tile
+    const int col0 = hf * half_cols;
+    float o[D0];
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
+    for (int i = 0; i < D0; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;                           // l: this thread's share of the row sum
     for (int j = 0; j < a.nkt; ++j) {
       mbar_wait(S_FULL, j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-      for (int c = 0; c < KT / 64; ++c) {
-        uint32_t rr[64];
-        tmem_ld64(tS + lane_off + c * 64, rr);
-#pragma unroll
-        for (int e = 0; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      // this thread's columns of S(j): read once, kept in registers across the max exchange
+      uint32_t rr[64];
+      tmem_ld16(tS + lane_off + col0, rr);
+      tmem_ld16(tS + lane_off + col0 + 16, rr + 16);
+      if (half_cols == 64) {
+        tmem_ld16(tS + lane_off + col0 + 32, rr + 32);
+        tmem_ld16(tS + lane_off + col0 + 48, rr + 48);
       }
+      tmem_ld_wait();
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      if (half_cols == 64) {
+#pragma unroll
+        for (int e = 32; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      }
+      float* xm = xmax + (j & 1) * 2 * QT;                  // double-buffered by tile parity
+      xm[hf * QT + r] = mx;
+      named_bar_sync(1, SOFTMAX_THREADS);
+      mx = fmaxf(mx, xm[(hf ^ 1) * QT + r]);
       // scale > 0, so max(s)*scale == max(s*scale)
       const float mnew = fmaxf(m, mx * a.scale);
       const float corr = __expf(m - mnew);
       float sum = 0.f;
-      for (int c = 0; c < KT / 64; ++c) {
-        uint32_t rr[64];
-        tmem_ld64(tS + lane_off + c * 64, rr);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 8; ++g) {
+        if (g < 4 || half_cols == 64) {
           float p[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
           }
           uint4 hv, lv;
           split8(p, hv, lv);
-          const size_t off = ((size_t)(c * 8 + g) * QT + r) * 16;
+          const size_t off = ((size_t)(col0 / 8 + g) * QT + r) * 16;
           *reinterpret_cast<uint4*>(ph + off) = hv;
           *reinterpret_cast<uint4*>(pl + off) = lv;
         }
@@ -246,27 +268,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       mbar_wait(O_FULL, j & 1);
       tc_fence_after();
       {
-        constexpr int G = (D % 32 == 0) ? 32 : 16;        // columns per wait
+        uint32_t ro[D0];
 #pragma unroll
-        for (int c = 0; c < D / G; ++c) {
-          uint32_t rr[G];
+        for (int c = 0; c < D0 / 16; ++c)
+          if (c * 16 < n_o) tmem_ld16(tO + lane_off + oc0 + c * 16, ro + c * 16);     // warp-uniform predicate
+        tmem_ld_wait();
 #pragma unroll
-          for (int q = 0; q < G / 16; ++q) tmem_ld16(tO + lane_off + c * G + q * 16, rr + q * 16);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < G; ++e) o[c * G + e] = fmaf(o[c * G + e], corr, __uint_as_float(rr[e]));
-        }
+        for (int e = 0; e < D0; ++e)
+          if (e < n_o) o[e] = fmaf(o[e], corr, __uint_as_float(ro[e]));
       }
     }
     tc_fence_before();
+    // row sum = the two halves' shares (same running maximum, so they simply add)
+    xsum[hf * QT + r] = l;
+    named_bar_sync(1, SOFTMAX_THREADS);
     if (q0 + r < a.T) {
-      const float inv = 1.0f / l;
-      float* op = a.out + ((long long)b * a.T + q0 + r) * a.C + h * D;
+      const float inv = 1.0f / (xsum[r] + xsum[QT + r]);
+      float* op = a.out + ((long long)b * a.T + q0 + r) * a.C + h * D + oc0;
 #pragma unroll
-      for (int c = 0; c < D; c += 4)
-        *reinterpret_cast<float4*>(op + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+      for (int c = 0; c < D0; c += 4)
+        if (c < n_o)
+          *reinterpret_cast<float4*>(op + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ================= image loader: one thread, cp.async.bulk global -> smem =================
     if (elect_one()) {
       const uint32_t qbytes = (uint32_t)q_image_bytes<D>(), kvbytes = (uint32_t)kv_image_bytes<D>(KT);
@@ -285,7 +309,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       }
     }
   } else if (elect_one()) {
-    // ================= MMA issuer (one elected lane of warp 5) =================
+    // ================= MMA issuer (one elected lane of warp 9) =================
     const uint32_t idesc_s = make_idesc_f16(QT, KT), idesc_o = make_idesc_f16(QT, D);
     const uint32_t q_lbo = QT * 16, k_lbo = (uint32_t)KT * 16, v_lbo = D * 16, p_lbo = QT * 16;
     const uint32_t sqh = smem_u32(qh), sql = smem_u32(ql), skh = smem_u32(kh), skl = smem_u32(kl);
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
@@ -345,7 +369,7 @@ int launch_d(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.dst2, "ATTENTION_UMMA: dst2 (operand-image scratch, mcvd_attention_scratch_bytes) is NULL");
   MCVD_CHECK((reinterpret_cast<uintptr_t>(op.dst2) & 15) == 0, "ATTENTION_UMMA: scratch must be 16-byte aligned");
   const size_t smem = 2 * ((size_t)(D / 8) * QT * 16 + (size_t)(D / 8) * a.KT * 16 + (size_t)(a.KT / 8) * D * 16 +
-                           (size_t)(a.KT / 8) * QT * 16) + 64;
+                           (size_t)(a.KT / 8) * QT * 16) + 64 + 6 * QT * sizeof(float);
   MCVD_CHECK(smem <= 227 * 1024, "ATTENTION_UMMA: %zu B of shared memory", smem);
   cudaError_t e = cudaFuncSetAttribute(k_attention_umma<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   MCVD_CHECK(e == cudaSuccess, "ATTENTION_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
