@@ -102,6 +102,17 @@ def test_validate_program_rejects_bad_ops_without_gpu():
     o.src0 = o.dst = buf.data_ptr()
     with pytest.raises(RuntimeError, match="multiples of 4"):
         lib.validate_program(lib.make_ops([o]), 1)
+    # tensor-core attention needs its operand-image scratch; the size helper and the launch count are host-only
+    o = lib.McvdOp()
+    o.kind, o.B, o.H, o.W, o.C0, o.i0, o.i1 = lib.OP_ATTENTION_UMMA, 2, 16, 16, 192, 2, 96
+    o.src0 = o.dst = buf.data_ptr()
+    with pytest.raises(RuntimeError, match="scratch"):
+        lib.validate_program(lib.make_ops([o]), 1)
+    o.dst2 = buf.data_ptr()
+    lib.validate_program(lib.make_ops([o]), 1)
+    assert lib.load().mcvd_count_launches(ctypes.byref(o), 1) == 2
+    assert lib.attention_scratch_bytes(2, 256, 192) == 4 * 2 * 192 * (256 + 2 * 256)
+    assert lib.attention_scratch_bytes(3, 64, 32) == 4 * 3 * 32 * (128 + 2 * 64)      # Q padded to a 128-row tile
 
 
 def test_product_path_fails_loudly_without_cuda():
