@@ -6,10 +6,10 @@
 //   grid = (ceil(T / 128), heads, B); one CTA owns 128 query rows and walks the keys in tiles of KT.
 //
 // Per key tile:   S = Q K^T   (tcgen05.mma, M=128, N=KT, K=d)          -> TMEM columns [0, KT)
-//                 P = exp(S*scale - m)  by the softmax warps (one thread per query row = TMEM lane:
-//                     no shuffles), written to smem as the A operand of the next MMA
+//                 P = exp(S*scale - m)  by the softmax warps (query row = TMEM lane: no shuffles),
+//                     written to smem as the A operand of the next MMA
 //                 O_tile = P V (M=128, N=d, K=KT)                       -> TMEM columns [KT, KT+d)
-//                 o = o * exp(m_old - m_new) + O_tile   in registers (d floats per thread)
+//                 o = o * exp(m_old - m_new) + O_tile   in registers
 // fp32 parity: q, k, v and p are split into fp16 hi + lo and every product is 3 MMAs
 // (hi*hi + lo*hi + hi*lo), fp32 accumulation -- same scheme as conv_umma.cu.
 //
@@ -160,15 +160,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS) k_attn_presplit(const AttnArgs 
     stage_v<D>(dst, dst + kv_image_bytes<D>(KT) / 2, base + 2 * a.C + (long long)kt * KT * C3, C3, KT, threadIdx.x,
                SPLIT_THREADS);
   }
-}
-
-// 64 consecutive TMEM columns of this thread's lane -> registers (one wait)
-__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t r[64]) {
-  tmem_ld16(taddr, r);
-  tmem_ld16(taddr + 16, r + 16);
-  tmem_ld16(taddr + 32, r + 32);
-  tmem_ld16(taddr + 48, r + 48);
-  tmem_ld_wait();
 }
 
 template <int D>
