@@ -163,6 +163,30 @@ def test_conditioning_and_shard_helpers():
 
 
 @pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
+@pytest.mark.parametrize("p_cond,p_fut,sync", [(0.0, 0.0, False), (0.5, 0.0, False), (0.5, 0.5, False),
+                                               (0.5, 0.5, True), (0.0, 1.0, False), (0.3, 1.0, False)])
+def test_conditioning_masks_match_reference_draw_for_draw(p_cond, p_fut, sync):
+    """Past / future masking of the paper's "general" models (reference runner:104-147): same Bernoulli draws in
+    the same order, so a seeded run of either implementation returns identical tensors."""
+    R = ref_import.ref_runner()
+    cfg = configs.workload("tiny")
+    cfg.data.num_frames_future = 2
+    cfg.data.prob_mask_sync = sync
+    n = cfg.data.num_frames_cond + cfg.data.num_frames + cfg.data.num_frames_future
+    X = detfill.normal("clips", (6, n, cfg.data.channels, 32, 32))
+    outs = []
+    for fn in (R.conditioning_fn, runner.conditioning_fn):
+        torch.manual_seed(7)
+        outs.append(fn(cfg, X, num_frames_pred=cfg.data.num_frames, prob_mask_cond=p_cond, prob_mask_future=p_fut))
+    (p0, c0, m0), (p1, c1, m1) = outs
+    assert torch.equal(p0, p1) and torch.equal(c0, c1) and c1.shape[1] == cfg.data.channels * (3 + 2)
+    assert (m0 is None and m1 is None) or torch.equal(m0, m1)
+    # unconditional models get every frame as the prediction target
+    u0, u1 = (fn(cfg, X, conditional=False) for fn in (R.conditioning_fn, runner.conditioning_fn))
+    assert torch.equal(u0[0], u1[0]) and u1[1] is None and u1[2] is None
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not on this box")
 def test_patch_shim_installs_and_falls_back_on_cpu():
     """mcvd_b200.patch swaps get_model / samplers inside the unmodified reference; on a CPU config it
     must hand back the reference module and the reference samplers' behaviour."""

@@ -35,6 +35,12 @@ def test_forward_lowering_matches_oracle_and_golden(name, conv_mode):
     P = net.engine().program(B)
     if conv_mode == "umma":
         assert P.n_umma > 0
+    # the lowered program is valid for the C ABI, and host and library agree on its kernel-launch count
+    from mcvd_b200 import lib
+    for arr, ops, n in ((P.step_arr, P.step_ops, P.step_launches), (P.cond_arr, P.cond_ops, P.cond_launches)):
+        if ops:
+            lib.validate_program(arr, len(ops))
+            assert lib.load().mcvd_count_launches(arr, len(ops)) == n >= len(ops)
 
 
 @pytest.mark.parametrize("name", ["tiny", "tiny_spade"])
