@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MCVD_ABI_VERSION 3
+#define MCVD_ABI_VERSION 4
 
 /* ---- op kinds ------------------------------------------------------------------------------- */
 enum {
@@ -58,7 +58,11 @@ enum {
    *   aux0 == NULL              : G = 1, S = 0
    * src0 = per-channel partials of the first tensor ([B,i0,C0]); src1/C1 = partials of a second tensor
    * (virtual concat) or NULL/0; i0 = chunks, f0 = eps.  Partials are per TENSOR, so a tensor consumed by
-   * several norms (skip connections) is scanned once. */
+   * several norms (skip connections) is scanned once.
+   * i4 / i5 != 0: src0 / src1 is not a chunk array but the int64 tile statistics a MCVD_OP_CONV_UMMA2
+   * epilogue wrote for that tensor, i4 / i5 = kernel size (1|3) of the producing conv (fixes the tile geometry).
+   * dst2 != NULL additionally receives the planar table [B][3][C] = mean | rstd*G | S read by
+   * MCVD_OP_CONV_UMMA2. */
   MCVD_OP_GN_FINALIZE = 6,
   /* normalise + FiLM (+ SPADE gamma/beta) + SiLU + optional 4x4 FIR up/down-sampling, fp32 NHWC in
    * and out.  get_act_norm.forward layerspp.py:518-549, MySPADE.forward :152-173 (norm part),
@@ -110,6 +114,21 @@ enum {
    * Head dim in {32,48,64,96,128}, H*W a multiple of the key tile (128, or 64 for head dim 128; 64 when
    * H*W = 64).  See mcvd_b200/csrc/attention_umma.cu. */
   MCVD_OP_ATTENTION_UMMA = 15,
+  /* MCVD_OP_CONV_UMMA on CTA pairs (tcgen05.mma.cta_group::2, M = 256 over the two SMs of a TPC; see
+   * mcvd_b200/csrc/conv_umma2.cu).  Same semantics and fields, except:
+   *   aux1 = norm table of (src0|src1) in the planar layout [B][3][C0+C1] = mean | rstd*G | S that
+   *          MCVD_OP_GN_FINALIZE writes to its dst2 (NULL: raw input);
+   *   w    = weights packed by mcvd_umma2_pack_weights for n tile i1 and K-block i2
+   *          (i2 = mcvd_umma2_plan(...); 0 skips the consistency check);
+   *   i3   = operand split: 3 (default, also 0) = hi*hi + lo*hi + hi*lo, 1 = drop hi*lo (fp16 weights),
+   *          2 = drop lo*hi (fp16 activations), 4 = hi*hi only -- accuracy experiments, DESIGN.md section 4;
+   *   dst2 = NULL, or int64 [tiles][NJ][2][Cout] receiving the GroupNorm partial sums of the stored output
+   *          (sum and sum of squares of round(x * 2^16), exact integer arithmetic; tiles = 128-position row
+   *          tiles of the padded-flat position space, NJ = 127 / Pimg + 2 image slots per tile,
+   *          mcvd_umma2_stats_bytes() bytes) -- nn.GroupNorm statistics of the NEXT act-norm
+   *          (layerspp.py:474-477) without re-reading the activation;
+   *   aux2 = NULL or int64 [grid][16] cycle counters (tools/umma_timing.py). */
+  MCVD_OP_CONV_UMMA2 = 16,
   MCVD_OP__COUNT
 };
 
@@ -143,6 +162,7 @@ typedef struct McvdOp {
   const void* src2;
   const void* src3;
   int32_t C2, C3;
+  int32_t i4, i5, i6, i7;   /* more per-kind integers (ABI v4)                                  */
 } McvdOp;
 
 /* Library / ABI identification. */
@@ -176,6 +196,23 @@ long long mcvd_umma_pack_weights(const float* w_taps, int taps, int Cin, int Cou
 /* Channels per K-block (32, 16, or 0 = unsupported) the tensor-core conv uses for sources with C0 / C1
  * channels; the packed weights must be produced with the same value. */
 int mcvd_umma_kblock(int C0, int C1);
+/* MCVD_OP_CONV_UMMA2 planning: channels per K-block (32 | 16, 0 = unsupported) for a conv of kernel size ks on
+ * H x W maps with sources of C0|C1 (+ shortcut C2|C3) channels, n tile `n_tile`, with / without epilogue
+ * statistics (the shared-memory plan depends on all of them); the weights must be packed with this value. */
+int mcvd_umma2_plan(int H, int W, int ks, int C0, int C1, int C2, int C3, int n_tile, int stats);
+/* The shared-memory plan behind mcvd_umma2_plan (diagnostics / tests; host arithmetic only): out[0..7] = K-block,
+ * slab rows, image stages, raw-ring stages, weight stages, image slots per tile, TMEM columns, dynamic shared
+ * memory bytes.  Returns 0, or -1 when the conv cannot run on this kernel. */
+int mcvd_umma2_plan_info(int H, int W, int ks, int C0, int C1, int C2, int C3, int n_tile, int stats, int* out);
+/* Bytes of the dst2 statistics array of a MCVD_OP_CONV_UMMA2 op. */
+long long mcvd_umma2_stats_bytes(int B, int H, int W, int ks, int Cout);
+/* Weight packing for MCVD_OP_CONV_UMMA2.  w_taps = fp32 [taps][Cin][Cout]; every (n tile, K-block, tap) becomes
+ * two shared-memory images (one per CTA of the pair, NT/2 output columns each).  A conv with a fused 1x1
+ * shortcut is packed with two calls into the same `out`: the main conv with stage_off = 0 and the shortcut
+ * with stage_off = (Cin_main / KB) * taps, both with per_unit = total stages of one n tile.  Returns the bytes
+ * this call fills (taps*Cin*Cout*4); out == NULL only queries. */
+long long mcvd_umma2_pack_weights(const float* w_taps, int taps, int Cin, int Cout, int n_tile, int k_block,
+                                  void* out, int scale_log2, int stage_off, int per_unit, void* stream);
 /* Bytes of dst2 scratch one MCVD_OP_ATTENTION_UMMA op with batch B, T = H*W tokens and C channels needs. */
 long long mcvd_attention_scratch_bytes(int B, int T, int C);
 

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libmcvd_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "conv_simt.cu", "conv_smalln.cu", "attention_simt.cu", "conv_umma.cu",
+SOURCES = ["api.cu", "elementwise.cu", "conv_simt.cu", "conv_smalln.cu", "attention_simt.cu", "conv_umma.cu", "conv_umma2.cu",
            "attention_umma.cu"]
 HEADERS = [os.path.join(CSRC, "mcvd_common.cuh"), os.path.join(CSRC, "umma_ptx.cuh"), os.path.join(os.path.dirname(HERE), "include", "mcvd_b200.h")]
 
@@ -39,9 +39,22 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
-        return LIB
+    """Compile and link under a cross-process file lock (torchrun starts one rank per GPU: with a missing or
+    stale library they would otherwise all write the same .o / .so); objects and the library are written to
+    temporary names and renamed into place, so a concurrent dlopen never sees a half-written file."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
+    if not force and not needs_build():          # another process may have built it while we waited for the lock
+        return LIB
     objs = []
     procs = []
     for src in sources():
@@ -50,19 +63,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(
                 os.path.getmtime(p) for p in [src] + HEADERS):
             continue
+        tmp = obj + f".tmp{os.getpid()}"
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, p in procs:
+               "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", tmp]
+        procs.append((src, tmp, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = None
+    for src, tmp, obj, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+            failed = failed or f"nvcc failed for {src}:\n{out}"
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            continue
+        os.replace(tmp, obj)
         if verbose or "warning" in out.lower():
             sys.stderr.write(out)
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static"]
+    if failed:
+        raise RuntimeError(failed)
+    tmp_lib = LIB + f".tmp{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-o", tmp_lib] + objs + ["-cudart", "static"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB)
     return LIB
 
 

@@ -29,6 +29,7 @@ static int dispatch(const McvdOp& op, cudaStream_t s) {
     case MCVD_OP_RESIZE_NEAREST: return launch_resize_nearest(op, s);
     case MCVD_OP_DIFFUSION_UPDATE: return launch_diffusion_update(op, s);
     case MCVD_OP_CONV_UMMA: return launch_conv_umma(op, s);
+    case MCVD_OP_CONV_UMMA2: return launch_conv_umma2(op, s);
     case MCVD_OP_CONV_SMALLN: return launch_conv_smalln(op, s);
     case MCVD_OP_COPY: return launch_copy(op, s);
     case MCVD_OP_ATTENTION_UMMA: return launch_attention_umma(op, s);
@@ -75,6 +76,7 @@ static int validate_one(const McvdOp& op, int idx) {
       break;
     case MCVD_OP_CONV_SIMT:
     case MCVD_OP_CONV_UMMA:
+    case MCVD_OP_CONV_UMMA2:
       if (!op.w || (op.i0 != 1 && op.i0 != 3)) {
         set_error("op %d CONV: null weights or kernel size %d", idx, op.i0);
         return -1;

@@ -224,42 +224,99 @@ int launch_gn_partial(const McvdOp& op, cudaStream_t s) {
 }
 
 // Pass 2: grid (groups, B); reduce partials, emit (mean, rstd, G, S) per channel.
-__global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__ part0,
-                                                     const double2* __restrict__ part1, float4* __restrict__ tab,
-                                                     const float* __restrict__ aux0, const float* __restrict__ aux1,
-                                                     int C0, int C1, int cg, int nchunk, int HW, float eps, int film,
-                                                     int film_stride, int film_off) {
-  int g = blockIdx.x, b = blockIdx.y;
-  const int C = C0 + C1;
-  int n = nchunk * cg;
-  double ds = 0.0, dq = 0.0;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int chunk = i / cg, c = g * cg + i % cg;
-    // per-channel partials live with the tensor that owns the channel (virtual concat of two tensors)
-    double2 v = (c < C0) ? part0[((long long)b * nchunk + chunk) * C0 + c]
-                         : part1[((long long)b * nchunk + chunk) * C1 + (c - C0)];
-    ds += v.x;
-    dq += v.y;
+// A source is either a chunk array of k_gn_partial (double2 [B][nchunk][C]) or the int64 tile statistics a
+// k_conv_umma2 epilogue wrote for that tensor ([tiles][NJ][2][C]: sum and sum of squares of round(x * 2^16) over
+// the rows of one 128-position tile that belong to one image).  Integer sums are exact, so the statistics do not
+// depend on where the image sits in the batch (clip sharding stays bit-exact).
+struct GnSrc {
+  const void* p;
+  int C;          // channels of this tensor
+  int ks;         // 0: chunk partials; 1 | 3: tile statistics of a conv with this kernel size
+};
+
+__device__ __forceinline__ void gn_tile_geometry(int ks, int H, int W, int& pimg, int& nj) {
+  pimg = ks == 3 ? (H + 1) * (W + 1) : H * W;
+  nj = 127 / pimg + 2;
+}
+
+__global__ void __launch_bounds__(128) k_gn_finalize(GnSrc s0, GnSrc s1, float4* __restrict__ tab,
+                                                     float* __restrict__ tab3, const float* __restrict__ aux0,
+                                                     const float* __restrict__ aux1, int B, int H, int W, int cg,
+                                                     int nchunk, float eps, int film, int film_stride, int film_off) {
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int C0 = s0.C, C = s0.C + s1.C, HW = H * W;
+  double ds = 0.0, dq = 0.0;                         // chunk-partial contributions
+  long long s1lo = 0, s1hi = 0;                      // tile statistics: 64-bit partials summed as 32-bit halves
+  unsigned long long s2lo = 0, s2hi = 0;
+  bool any_tiles = false;
+  for (int ci = 0; ci < cg; ++ci) {                  // the group may straddle the two tensors of a virtual concat
+    const int c = g * cg + ci;
+    const GnSrc& sr = (c < C0) ? s0 : s1;
+    const int cl = (c < C0) ? c : c - C0;
+    if (sr.ks == 0) {
+      const double2* part = reinterpret_cast<const double2*>(sr.p);
+      for (int chunk = threadIdx.x; chunk < nchunk; chunk += blockDim.x) {
+        const double2 v = part[((long long)b * nchunk + chunk) * sr.C + cl];
+        ds += v.x;
+        dq += v.y;
+      }
+    } else {
+      any_tiles = true;
+      int pimg, nj;
+      gn_tile_geometry(sr.ks, H, W, pimg, nj);
+      const long long q0 = (long long)b * pimg, q1 = q0 + pimg - 1;
+      const int t_lo = (int)(q0 >> 7), t_hi = (int)(q1 >> 7);
+      const long long* st = reinterpret_cast<const long long*>(sr.p);
+      for (int t = t_lo + threadIdx.x; t <= t_hi; t += blockDim.x) {
+        long long tb0 = ((long long)t << 7) / pimg;
+        if (tb0 > B - 1) tb0 = B - 1;
+        const int jj = b - (int)tb0;
+        const long long* e = st + (((long long)t * nj + jj) * 2) * sr.C + cl;
+        const long long v1 = e[0];
+        const unsigned long long v2 = (unsigned long long)e[sr.C];
+        s1lo += (long long)(v1 & 0xffffffffLL);
+        s1hi += v1 >> 32;
+        s2lo += v2 & 0xffffffffULL;
+        s2hi += v2 >> 32;
+      }
+    }
   }
-  __shared__ double sh[2][4];
+  __shared__ double shd[2][4];
+  __shared__ long long shi[4][4];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     ds += __shfl_xor_sync(0xffffffffu, ds, o);
     dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    s1lo += __shfl_xor_sync(0xffffffffu, s1lo, o);
+    s1hi += __shfl_xor_sync(0xffffffffu, s1hi, o);
+    s2lo += __shfl_xor_sync(0xffffffffu, s2lo, o);
+    s2hi += __shfl_xor_sync(0xffffffffu, s2hi, o);
   }
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { sh[0][warp] = ds; sh[1][warp] = dq; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    shd[0][warp] = ds; shd[1][warp] = dq;
+    shi[0][warp] = s1lo; shi[1][warp] = s1hi; shi[2][warp] = (long long)s2lo; shi[3][warp] = (long long)s2hi;
+  }
   __syncthreads();
-  ds = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3];
-  dq = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
-  double cnt = (double)HW * (double)cg;
-  double mean = ds / cnt;
+  ds = shd[0][0] + shd[0][1] + shd[0][2] + shd[0][3];
+  dq = shd[1][0] + shd[1][1] + shd[1][2] + shd[1][3];
+  if (any_tiles) {
+    const long long a1lo = shi[0][0] + shi[0][1] + shi[0][2] + shi[0][3];
+    const long long a1hi = shi[1][0] + shi[1][1] + shi[1][2] + shi[1][3];
+    const unsigned long long a2lo = (unsigned long long)(shi[2][0] + shi[2][1] + shi[2][2] + shi[2][3]);
+    const unsigned long long a2hi = (unsigned long long)(shi[3][0] + shi[3][1] + shi[3][2] + shi[3][3]);
+    // hi * 2^32 and lo are exact doubles; their sum is one correctly rounded addition of the exact total
+    ds += ((double)a1hi * 4294967296.0 + (double)a1lo) * (1.0 / 65536.0);
+    dq += ((double)a2hi * 4294967296.0 + (double)a2lo) * (1.0 / 4294967296.0);
+  }
+  const double cnt = (double)HW * (double)cg;
+  const double mean = ds / cnt;
   double var = dq / cnt - mean * mean;
   if (var < 0.0) var = 0.0;
-  float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  float fmean = (float)mean;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float fmean = (float)mean;
   for (int ci = threadIdx.x; ci < cg; ci += blockDim.x) {
-    int c = g * cg + ci;
+    const int c = g * cg + ci;
     float G = 1.f, S = 0.f;
     if (aux0) {
       if (film) {
@@ -271,6 +328,12 @@ __global__ void __launch_bounds__(128) k_gn_finalize(const double2* __restrict__
       }
     }
     tab[(long long)b * C + c] = make_float4(fmean, rstd, G, S);
+    if (tab3) {
+      float* t3 = tab3 + (long long)b * 3 * C + c;
+      t3[0] = fmean;
+      t3[C] = rstd * G;
+      t3[2 * C] = S;
+    }
   }
 }
 
@@ -281,10 +344,19 @@ int launch_gn_finalize(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.C1 == 0 || op.src1, "GN_FINALIZE: second partial array missing");
   int film = (op.flags & MCVD_F_FILM) ? 1 : 0;
   MCVD_CHECK(!op.aux0 || film || op.aux1, "GN_FINALIZE: affine needs weight and bias");
+  MCVD_CHECK((op.i4 == 0 || op.i4 == 1 || op.i4 == 3) && (op.i5 == 0 || op.i5 == 1 || op.i5 == 3),
+             "GN_FINALIZE: source kinds (%d, %d) must be 0 (chunks), 1 or 3 (conv tile statistics)", op.i4, op.i5);
+  for (int k = 0; k < 2; ++k) {
+    const int ks = k ? op.i5 : op.i4;
+    if (ks == 0 || (k && op.C1 == 0)) continue;
+    const long long pimg = ks == 3 ? (long long)(op.H + 1) * (op.W + 1) : (long long)op.H * op.W;
+    MCVD_CHECK(pimg >= 64, "GN_FINALIZE: tile statistics need images of >= 64 positions (%dx%d)", op.H, op.W);
+  }
+  MCVD_CHECK((op.i4 != 0 && (op.C1 == 0 || op.i5 != 0)) || op.i0 >= 1, "GN_FINALIZE: chunks < 1");
+  GnSrc s0{op.src0, op.C0, op.i4}, s1{op.src1, op.C1, op.C1 > 0 ? op.i5 : 0};
   dim3 grid(C / cg, op.B);
-  k_gn_finalize<<<grid, 128, 0, s>>>((const double2*)op.src0, (const double2*)op.src1, (float4*)op.dst,
-                                     (const float*)op.aux0, (const float*)op.aux1, op.C0, op.C1, cg, op.i0,
-                                     op.H * op.W, op.f0, film, op.i2, op.i3);
+  k_gn_finalize<<<grid, 128, 0, s>>>(s0, s1, (float4*)op.dst, (float*)op.dst2, (const float*)op.aux0,
+                                     (const float*)op.aux1, op.B, op.H, op.W, cg, op.i0, op.f0, film, op.i2, op.i3);
   MCVD_CUDA_LAUNCH_CHECK("gn_finalize");
   return 0;
 }

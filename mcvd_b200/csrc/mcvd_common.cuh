@@ -45,6 +45,7 @@ int launch_attention(const McvdOp& op, cudaStream_t s);
 int launch_resize_nearest(const McvdOp& op, cudaStream_t s);
 int launch_diffusion_update(const McvdOp& op, cudaStream_t s);
 int launch_conv_umma(const McvdOp& op, cudaStream_t s);
+int launch_conv_umma2(const McvdOp& op, cudaStream_t s);
 int launch_conv_smalln(const McvdOp& op, cudaStream_t s);
 int launch_copy(const McvdOp& op, cudaStream_t s);
 int launch_attention_umma(const McvdOp& op, cudaStream_t s);

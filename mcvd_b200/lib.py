@@ -27,6 +27,7 @@ OP_CONV_UMMA = 12
 OP_CONV_SMALLN = 13
 OP_COPY = 14
 OP_ATTENTION_UMMA = 15
+OP_CONV_UMMA2 = 16
 
 F_ACT_IN = 1 << 0
 F_ACT_OUT = 1 << 1
@@ -36,11 +37,11 @@ F_FILM = 1 << 4
 F_CLIP = 1 << 5
 F_PHILOX = 1 << 6
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = ["mcvd_abi_version", "mcvd_sizeof_op", "mcvd_last_error", "mcvd_device_arch", "mcvd_run_program",
            "mcvd_validate_program", "mcvd_count_launches", "mcvd_umma_pack_weights", "mcvd_umma_kblock",
-           "mcvd_attention_scratch_bytes"]
+           "mcvd_attention_scratch_bytes", "mcvd_umma2_plan", "mcvd_umma2_plan_info", "mcvd_umma2_stats_bytes", "mcvd_umma2_pack_weights"]
 
 
 class McvdOp(C.Structure):
@@ -55,6 +56,7 @@ class McvdOp(C.Structure):
         ("aux0", C.c_void_p), ("aux1", C.c_void_p), ("aux2", C.c_void_p),
         ("dst", C.c_void_p), ("dst2", C.c_void_p),
         ("src2", C.c_void_p), ("src3", C.c_void_p), ("C2", C.c_int32), ("C3", C.c_int32),
+        ("i4", C.c_int32), ("i5", C.c_int32), ("i6", C.c_int32), ("i7", C.c_int32),
     ]
 
 
@@ -75,12 +77,19 @@ def load():
         if _lib is not None:
             return _lib
         path = _build.LIB
-        try:
-            if _build.needs_build():
+        if _build.needs_build():
+            try:
+                nvcc = _build._nvcc()
+            except RuntimeError as e:       # no compiler on this box: the prebuilt library (if any) is all there is
+                nvcc = None
+                if not os.path.exists(path):
+                    raise RuntimeError(f"mcvd_b200: CUDA library missing and cannot be built: {e}") from e
+                import warnings
+                warnings.warn("mcvd_b200: sources are newer than the prebuilt library and nvcc is not available; "
+                              "using the prebuilt library")
+            if nvcc is not None:
+                # a compiler exists and the library is stale: a failed rebuild must not silently fall back to it
                 _build.build()
-        except Exception as e:  # no nvcc on this box: use the prebuilt library if there is one
-            if not os.path.exists(path):
-                raise RuntimeError(f"mcvd_b200: CUDA library missing and cannot be built: {e}") from e
         if not os.path.exists(path):
             raise RuntimeError(f"mcvd_b200: CUDA library not found at {path}")
         lib = C.CDLL(path)
@@ -101,6 +110,15 @@ def load():
         lib.mcvd_umma_kblock.argtypes = [C.c_int, C.c_int]
         lib.mcvd_attention_scratch_bytes.restype = C.c_longlong
         lib.mcvd_attention_scratch_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.mcvd_umma2_plan.restype = C.c_int
+        lib.mcvd_umma2_plan.argtypes = [C.c_int] * 9
+        lib.mcvd_umma2_plan_info.restype = C.c_int
+        lib.mcvd_umma2_plan_info.argtypes = [C.c_int] * 9 + [C.POINTER(C.c_int)]
+        lib.mcvd_umma2_stats_bytes.restype = C.c_longlong
+        lib.mcvd_umma2_stats_bytes.argtypes = [C.c_int] * 5
+        lib.mcvd_umma2_pack_weights.restype = C.c_longlong
+        lib.mcvd_umma2_pack_weights.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_void_p]
         if lib.mcvd_abi_version() != ABI_VERSION:
             raise RuntimeError("mcvd_b200: ABI version mismatch between the Python binding and the library")
         if lib.mcvd_sizeof_op() != C.sizeof(McvdOp):
@@ -138,3 +156,20 @@ def umma_kblock(c0: int, c1: int) -> int:
 def attention_scratch_bytes(B: int, T: int, C: int) -> int:
     """bytes of ``dst2`` scratch an OP_ATTENTION_UMMA op needs (fp16 hi/lo operand images of q, k, v)"""
     return int(load().mcvd_attention_scratch_bytes(B, T, C))
+
+
+def umma2_plan(H: int, W: int, ks: int, c0: int, c1: int, c2: int, c3: int, n_tile: int, stats: bool) -> int:
+    """channels per K-block (32 | 16 | 0 = not runnable) of an OP_CONV_UMMA2 op; host arithmetic only"""
+    return int(load().mcvd_umma2_plan(H, W, ks, c0, c1, c2, c3, n_tile, 1 if stats else 0))
+
+
+def umma2_stats_bytes(B: int, H: int, W: int, ks: int, cout: int) -> int:
+    return int(load().mcvd_umma2_stats_bytes(B, H, W, ks, cout))
+
+
+def umma2_plan_info(H, W, ks, c0, c1, c2, c3, n_tile, stats):
+    """dict of the shared-memory plan (K-block, slab rows, ring depths, bytes) or None"""
+    out = (C.c_int * 8)()
+    if load().mcvd_umma2_plan_info(H, W, ks, c0, c1, c2, c3, n_tile, 1 if stats else 0, out) != 0:
+        return None
+    return dict(zip(("kb", "hp", "sa", "r", "nb", "nj", "tmem_cols", "smem"), list(out)))

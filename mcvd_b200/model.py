@@ -153,6 +153,13 @@ class UNetMore_DDPM(nn.Module):
         self._engine = None          # device / dtype change invalidates packed weights and buffers
         return r
 
+    def _replicate_for_data_parallel(self):
+        """``torch.nn.DataParallel`` shallow-copies the module per GPU (reference runners/ncsn_runner.py:1377);
+        every replica must lower and pack for ITS device, not share device 0's engine."""
+        r = super()._replicate_for_data_parallel()
+        r._engine = None
+        return r
+
     def forward(self, x, y, cond=None, cond_mask=None):
         """eps = net(x_t, t, cond).  x [B, C*F, S, S] fp32 NCHW, y [B] (int64 or float), cond
         [B, C*Fc, S, S] or None.  ``cond_mask`` only matters for ``cond_emb=True`` nets, which are not

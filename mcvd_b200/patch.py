@@ -44,10 +44,14 @@ def install(verbose: bool = True):
         @functools.wraps(ref_fn)
         def sampler(x_mod, scorenet, *a, **kw):
             net = scorenet.module if hasattr(scorenet, "module") else scorenet
-            use_fast = isinstance(net, fast_model.UNetMore_DDPM) and x_mod.is_cuda and not kw.get("gamma", False)
-            if isinstance(net, fast_model.UNetMore_DDPM) and not use_fast:
-                raise RuntimeError("mcvd_b200 module used with sampler options the fast path does not cover "
-                                   "(gamma); build the reference model for those")
+            is_fast = isinstance(net, fast_model.UNetMore_DDPM)
+            if is_fast and kw.get("gamma", False):
+                raise RuntimeError("mcvd_b200 module used with a sampler option the fast path does not cover "
+                                   "(gamma=True); build the reference model for it")
+            if is_fast and not x_mod.is_cuda and next(net.parameters()).device.type != "cuda":
+                raise RuntimeError("mcvd_b200 module on a CPU device: the fast path is CUDA (sm_100a) only and has "
+                                   "no CPU fallback; build the reference model for CPU runs")
+            use_fast = is_fast
             return (fast_fn if use_fast else ref_fn)(x_mod, scorenet, *a, **kw)
         return sampler
 

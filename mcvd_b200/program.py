@@ -108,7 +108,9 @@ class Engine:
             if cc < 100:
                 raise RuntimeError(f"mcvd_b200 kernels are built for sm_100a only (device reports sm_{cc}: "
                                    f"{lib.last_error()})")
-        self.conv_mode = os.environ.get("MCVD_CONV", "umma").lower()       # 'umma' | 'simt'
+        # 'umma2' (CTA-pair tcgen05 kernel, default) | 'umma' (round-1 single-CTA kernel) | 'simt' (CUDA cores)
+        self.conv_mode = os.environ.get("MCVD_CONV", "umma2").lower()
+        self.split_mode = int(os.environ.get("MCVD_SPLIT", "3"))            # operand split (accuracy experiments)
         self.attn_mode = os.environ.get("MCVD_ATTN", "umma").lower()        # 'umma' | 'simt'
         self.use_graph = os.environ.get("MCVD_GRAPH", "1") != "0"
         self.packed: Dict[str, object] = {}
@@ -117,15 +119,32 @@ class Engine:
         self.launches_last_forward = 0
 
     # ------------------------------------------------------------------------------ weights
+    MAX_PROGRAMS = 3                 # lowered programs (one per batch size) kept alive; least recently used goes first
+
     def _version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.module.parameters())
+        """Fingerprint of the parameter VALUES.  ``Tensor._version`` is not enough: the reference's
+        ``EMAHelper.ema`` (models/ema.py:23-28) writes through ``param.data.copy_``, and ``.data`` carries its own
+        version counter, so the parameter's stays put.  Two multi-tensor norm launches (L2 and L1 of every
+        parameter, ~0.1 ms for 50 M parameters) and one comparison on the device; called once per sampler call /
+        module forward, never inside the step loop."""
+        ps = [p.detach() for p in self.module.parameters()]
+        ids = tuple((p.data_ptr(), tuple(p.shape)) for p in ps)
+        with torch.no_grad():
+            fp = torch.stack(list(torch._foreach_norm(ps, 2)) + list(torch._foreach_norm(ps, 1))).double()
+        return ids, fp
+
+    def invalidate(self):
+        """Forget packed weights, lowered programs and captured graphs (call after changing parameters in a way
+        the fingerprint cannot see, e.g. permuting values inside one tensor)."""
+        self.packed_version = None
 
     def _sd(self, key):
         return self._params[key]
 
     def ensure_packed(self):
         v = self._version()
-        if self.packed_version == v:
+        if self.packed_version is not None and self.packed_version[0] == v[0] and \
+                torch.equal(self.packed_version[1], v[1]):
             return
         self._params = {k: p.detach() for k, p in self.module.named_parameters()}
         self.packed = {}
@@ -200,14 +219,52 @@ class Engine:
             parts.append(out.view(n_nt, -1))
         return torch.cat(parts, dim=1).contiguous().view(-1), float(2.0 ** (-k))
 
+    def _pack_umma2(self, taps: torch.Tensor, taps_sc: Optional[torch.Tensor], nt: int, kb: int):
+        """CTA-pair weight images (conv_umma2.cu): main conv stages, then the fused 1x1 shortcut's, per n tile."""
+        if self.backend is not None:
+            flat = taps.reshape(-1) if taps_sc is None else torch.cat([taps.reshape(-1), taps_sc.reshape(-1)])
+            t, _ = self.backend.pack_umma(flat.contiguous(), nt, kb)
+            return t, 1.0
+        amax = float(taps.abs().max().item())
+        if taps_sc is not None:
+            amax = max(amax, float(taps_sc.abs().max().item()))
+        k = 0 if amax == 0.0 else int(math.floor(math.log2(512.0 / amax)))
+        k = max(-24, min(24, k))
+        T, I, O = taps.shape
+        isc = 0 if taps_sc is None else taps_sc.shape[1]
+        per_unit = (I // kb) * T + isc // kb
+        out = torch.empty((T * I + isc) * O * 4, device=taps.device, dtype=torch.uint8)
+        with self._devctx():
+            rc = self.lib.mcvd_umma2_pack_weights(taps.data_ptr(), T, I, O, nt, kb, out.data_ptr(), k, 0, per_unit,
+                                                  self._stream())
+            if rc >= 0 and taps_sc is not None:
+                rc = self.lib.mcvd_umma2_pack_weights(taps_sc.data_ptr(), 1, isc, O, nt, kb, out.data_ptr(), k,
+                                                      (I // kb) * T, per_unit, self._stream())
+        if rc < 0:
+            raise RuntimeError(f"mcvd_b200 umma2_pack_weights failed: {lib.last_error()}")
+        return out, float(2.0 ** (-k))
+
     # ------------------------------------------------------------------------------ lowering
-    def program(self, B: int) -> Program:
-        self.ensure_packed()
-        if B not in self.programs:
-            with self._devctx():
-                self.programs[B] = self._build(B)
-            if self.backend is not None:
-                self._register_all(self.programs[B])
+    def program(self, B: int, check_weights: bool = True) -> Program:
+        """The lowered program for batch size B.  Every program owns its activation buffers (a few GB at the
+        BASELINE batch sizes), so only MAX_PROGRAMS are kept: uneven shards / last batches evict the least
+        recently used one instead of piling up."""
+        if B <= 0:
+            raise ValueError(f"mcvd_b200: batch size {B} (an empty shard?) cannot be lowered")
+        if check_weights or self.packed_version is None:
+            self.ensure_packed()
+        if B in self.programs:
+            self.programs[B] = self.programs.pop(B)            # most recently used last
+            return self.programs[B]
+        while len(self.programs) >= self.MAX_PROGRAMS:
+            old = next(iter(self.programs))
+            del self.programs[old]
+            if self.device.type == "cuda":
+                torch.cuda.empty_cache()
+        with self._devctx():
+            self.programs[B] = self._build(B)
+        if self.backend is not None:
+            self._register_all(self.programs[B])
         return self.programs[B]
 
     def _register_all(self, P):
@@ -257,8 +314,10 @@ class Engine:
 
         # ---- convolution (tensor-core or CUDA-core) -------------------------------------------
         def conv(ops, key, src: Src, H: int, cout: int, ks: int, wname: str, bname: str, residual=None,
-                 scale=1.0, tab=None, act_in=False, act_out=False, nin=False, wcat=None, bcat=None, shortcut=None):
-            """dst = scale * (conv(act(norm(src))) + bias + residual [+ conv1x1(shortcut src)])."""
+                 scale=1.0, tab=None, act_in=False, act_out=False, nin=False, wcat=None, bcat=None, shortcut=None,
+                 stats=False):
+            """dst = scale * (conv(act(norm(src))) + bias + residual [+ conv1x1(shortcut src)]).
+            stats: the output feeds a GroupNorm -- let the conv epilogue emit its partial sums."""
             if wcat is not None:
                 taps, bias = wcat, bcat
             elif nin:
@@ -269,8 +328,40 @@ class Engine:
                 bias = sd(bname).float().contiguous()
             keep(bias)
             dst = f32(B, H, H, cout)
-            kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
             nt = _pick_nt(cout) if cout % 16 == 0 else 0
+            if self.conv_mode == "umma2" and nt:
+                sc_src = sc_taps = None
+                c2 = c3 = 0
+                if shortcut is not None:
+                    sc_src, sc_w, sc_b = shortcut
+                    c2, c3 = sc_src.c0, sc_src.c1
+                pimg = (H + 1) * (H + 1) if ks == 3 else H * H
+                want_stats = bool(stats and pimg >= 64)
+                kb = lib.umma2_plan(H, H, ks, src.c0, src.c1, c2, c3, nt, want_stats)
+                if kb:
+                    if shortcut is not None:
+                        sc_taps = self._conv_taps(sd(sc_w))
+                        bias = keep((bias + sd(sc_b).float()).contiguous())
+                    pk = (key, "umma2", nt, kb, shortcut is not None)
+                    if pk not in self.packed:
+                        self.packed[pk] = self._pack_umma2(taps, sc_taps, nt, kb)
+                    wp, wscale = self.packed[pk]
+                    fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
+                    kw2 = {}
+                    if shortcut is not None:
+                        kw2 = dict(src2=sc_src.t0, src3=sc_src.t1, C2=c2, C3=c3)
+                    st = None
+                    if want_stats:
+                        st = keep(torch.zeros(lib.umma2_stats_bytes(B, H, H, ks, cout) // 8, device=dev,
+                                              dtype=torch.int64))
+                        stats_of[dst.data_ptr()] = (st, ks)
+                    emit(ops, lib.OP_CONV_UMMA2, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=nt, i2=kb,
+                         i3=self.split_mode, f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias,
+                         aux0=residual, aux1=None if tab is None else tab3_of[tab.data_ptr()], dst=dst, dst2=st,
+                         flags=fl, **kw2)
+                    P.n_umma += 1
+                    return dst
+            kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
             sc = None
             if shortcut is not None:                       # (Src, wname, bname): 1x1 Conv_2 of the skip branch
                 sc_src, sc_w, sc_b = shortcut
@@ -328,14 +419,28 @@ class Engine:
                 part_cache[key] = part
             return part_cache[key]
 
+        stats_of: Dict[int, Tuple[torch.Tensor, int]] = {}     # tensor -> (conv-epilogue tile statistics, conv ks)
+        tab3_of: Dict[int, torch.Tensor] = {}                   # float4 table -> planar table (CONV_UMMA2 reads it)
+
+        def stat_source(ops, t: torch.Tensor, C: int, H: int, nchunk: int):
+            """(array, kind): the producing conv's epilogue statistics (kind = its kernel size) when it wrote
+            them, else the chunk partials of a separate pass over the tensor (kind 0)"""
+            if t.data_ptr() in stats_of:
+                return stats_of[t.data_ptr()]
+            return partials_of(ops, t, C, H, nchunk), 0
+
         def norm_table(ops, src: Src, H: int, eps: float, film_off=None, affine=None):
             C = src.C
             cg = C // arch.num_groups(C)
             nchunk = gn_chunks(H * H)
             tab = f32(B, C, 4)
-            p0 = partials_of(ops, src.t0, src.c0, H, nchunk)
-            p1 = partials_of(ops, src.t1, src.c1, H, nchunk) if src.t1 is not None else None
-            kw = dict(H=H, W=H, C0=src.c0, C1=src.c1, i0=nchunk, i1=cg, f0=eps, src0=p0, src1=p1, dst=tab)
+            p0, k0 = stat_source(ops, src.t0, src.c0, H, nchunk)
+            p1, k1 = stat_source(ops, src.t1, src.c1, H, nchunk) if src.t1 is not None else (None, 0)
+            kw = dict(H=H, W=H, C0=src.c0, C1=src.c1, i0=nchunk, i1=cg, f0=eps, src0=p0, src1=p1, dst=tab, i4=k0,
+                      i5=k1)
+            if self.conv_mode == "umma2":
+                tab3_of[tab.data_ptr()] = f32(B, 3, C)
+                kw["dst2"] = tab3_of[tab.data_ptr()]
             if film_off is not None:
                 kw.update(aux0=P.film, i2=ns.film_total, i3=film_off, flags=lib.F_FILM)
                 if ops is step:
@@ -375,7 +480,7 @@ class Engine:
         P.out = f32(B, ns.out_ch, S, S)
         # skinny first / last convs: zero-pad K (input channels) / N (output channels) to 16 so they run on the
         # tensor-core kernel instead of the CUDA-core ones
-        tc_edges = self.conv_mode == "umma"
+        tc_edges = self.conv_mode in ("umma", "umma2")
         in_pad = (ns.in_ch + 15) // 16 * 16 if tc_edges else ns.in_ch
         out_pad = (ns.out_ch + 15) // 16 * 16 if tc_edges else ns.out_ch
         P.noise = f32(B, ns.out_ch, S, S)
@@ -423,10 +528,11 @@ class Engine:
                      aux2=b0, dst=a0, dst2=xs, flags=lib.F_ACT_OUT | resample)
                 if resample:
                     sc_src = Src(xs, Cin)
-                h = conv(step, pre + "Conv_0", Src(a0, Cin), H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias")
+                h = conv(step, pre + "Conv_0", Src(a0, Cin), H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias",
+                         stats=True)
             else:
                 h = conv(step, pre + "Conv_0", src, H, Cout, 3, pre + "Conv_0.weight", pre + "Conv_0.bias", tab=tab0,
-                         act_in=True)
+                         act_in=True, stats=True)
             tab1 = norm_table(step, Src(h, Cout), H, eps, film_off=ms.film_off[1])
             shortcut = res = None
             if ms.has_shortcut:                      # Conv_2 rides along Conv_1 as a second K-segment
@@ -440,9 +546,9 @@ class Engine:
                 emit(step, lib.OP_APPLY, H=H, W=H, C0=Cout, src0=h, aux0=tab1, aux1=g1, aux2=b1, dst=a1,
                      flags=lib.F_ACT_OUT)
                 return conv(step, pre + "Conv_1", Src(a1, Cout), H, Cout, 3, pre + "Conv_1.weight",
-                            pre + "Conv_1.bias", residual=res, scale=INV_SQRT2, shortcut=shortcut)
+                            pre + "Conv_1.bias", residual=res, scale=INV_SQRT2, shortcut=shortcut, stats=True)
             return conv(step, pre + "Conv_1", Src(h, Cout), H, Cout, 3, pre + "Conv_1.weight", pre + "Conv_1.bias",
-                        residual=res, scale=INV_SQRT2, tab=tab1, act_in=True, shortcut=shortcut)
+                        residual=res, scale=INV_SQRT2, tab=tab1, act_in=True, shortcut=shortcut, stats=True)
 
         attn_scratch = [None]
 
@@ -470,7 +576,7 @@ class Engine:
                 emit(step, lib.OP_ATTENTION, H=H, W=H, C0=C, i0=ms.heads, i1=d, f0=float(int(d) ** (-0.5)),
                      src0=qkv, dst=att)
             return conv(step, pre + "NIN_3", Src(att, C), H, C, 1, pre + "NIN_3.W", pre + "NIN_3.b", residual=x,
-                        scale=INV_SQRT2, nin=True)
+                        scale=INV_SQRT2, nin=True, stats=True)
 
         w_first = self._conv_taps(sd("unet.all_modules.2.weight"))
         if in_pad != ns.in_ch:
@@ -478,7 +584,7 @@ class Engine:
             wp_[:, :ns.in_ch] = w_first
             w_first = wp_
         h = conv(step, "first", Src(xin, in_pad), S, ns.nf, 3, None, None, wcat=w_first,
-                 bcat=sd("unet.all_modules.2.bias").float().contiguous())
+                 bcat=sd("unet.all_modules.2.bias").float().contiguous(), stats=True)
         hs: List[Tuple[torch.Tensor, int]] = [(h, ns.nf)]
         cur, cur_c = h, ns.nf
         for ms in mods[3:-2]:

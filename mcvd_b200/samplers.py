@@ -50,24 +50,33 @@ class _Loop:
     def __init__(self, x_mod, scorenet, cond):
         self.net = _unwrap(scorenet)
         self.eng = self.net.engine()
-        if not x_mod.is_cuda and self.eng.backend is None:
-            raise RuntimeError("mcvd_b200 samplers run on CUDA tensors only (no CPU fallback)")
+        # the engine refuses to exist off-GPU (no CPU fallback); a CPU x_mod is staged to its device and the
+        # result is returned on x_mod's device, as the reference samplers do
         self.dev = self.eng.device
+        self.out_dev = x_mod.device              # results go back to the caller's device (reference contract)
         self.B = x_mod.shape[0]
         self.shape = x_mod.shape
         self.launches = 0
-        self._ctx = self.eng._devctx()
-        self._ctx.__enter__()
-        self.P = self.eng.program(self.B)
         if self.eng.spec.cond_ch > 0 and cond is None:
             raise RuntimeError("mcvd_b200: cond is required by this network")
-        self.eng.set_inputs(self.P, x=x_mod.float(), cond=None if cond is None else cond.float())
-        self.eng.run_cond(self.P)
-        self.launches += self.P.cond_launches
-        self.u = self.P.update_arr[0]
+        self._ctx = self.eng._devctx()
+        self._ctx.__enter__()
+        try:                                     # anything below may raise (build failure, OOM): do not leak the
+            self.P = self.eng.program(self.B)    # current-device context
+            self.eng.set_inputs(self.P, x=x_mod.to(self.dev).float(),
+                                cond=None if cond is None else cond.to(self.dev).float())
+            self.eng.run_cond(self.P)
+            self.launches += self.P.cond_launches
+            self.u = self.P.update_arr[0]
+        except BaseException:
+            self._ctx.__exit__(None, None, None)
+            raise
 
     def close(self):
         self._ctx.__exit__(None, None, None)
+
+    def result(self, t):
+        return t.to(self.out_dev)
 
     def eps(self, t):
         """eps = net(x_state, t, cond) into P.eps_nhwc (x_state = P.x_in)."""
@@ -185,7 +194,7 @@ def ddpm_sampler(x_mod, scorenet, cond=None, just_beta=False, final_only=False, 
                 images.append(lp.state().to("cpu"))
         ddpm_sampler.last_launches = lp.launches
         if final_only:
-            return lp.state().unsqueeze(0)
+            return lp.result(lp.state().unsqueeze(0))
         return torch.stack(images)
     finally:
         lp.close()
@@ -225,7 +234,7 @@ def ddim_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, sub
             if not final_only:
                 images.append(lp.state().to("cpu"))
         if final_only:
-            return lp.state().unsqueeze(0)
+            return lp.result(lp.state().unsqueeze(0))
         return torch.stack(images)
     finally:
         lp.close()
@@ -266,7 +275,7 @@ def FPNDM_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, su
             x_next = x + (an - at) * (cx * x - ce * et)
             return x_next.clip_(-1, 1) if clip_before else x_next
 
-        x = x_mod.float()
+        x = x_mod.to(lp.dev).float()             # eps tensors live on the engine's device; keep x there too
         ets: List[torch.Tensor] = []
         images = []
         for i in range(len(steps)):
@@ -291,7 +300,7 @@ def FPNDM_sampler(x_mod, scorenet, cond=None, final_only=False, denoise=True, su
             if not final_only:
                 images.append(x.to("cpu"))
         if final_only:
-            return x.reshape(lp.shape).unsqueeze(0)
+            return lp.result(x.reshape(lp.shape).unsqueeze(0))
         return torch.stack(images)
     finally:
         lp.close()

@@ -91,6 +91,31 @@ class Interpreter:
             xc = y.reshape(B, C, H, W)
         self.get(dst, B * H * W * C).copy_(xc.permute(0, 2, 3, 1).reshape(-1))
 
+    @staticmethod
+    def _tile_geometry(B, H, W, ks):
+        """(positions per image, image slots per 128-position tile, tiles) of the padded-flat position space of a
+        CONV_UMMA2 of kernel size ks (csrc/conv_umma2.cu)"""
+        pimg = (H + 1) * (W + 1) if ks == 3 else H * W
+        return pimg, 127 // pimg + 2, 2 * ((B * pimg + 255) // 256)
+
+    def _tile_stats(self, op, y):
+        """CONV_UMMA2 epilogue statistics: int64 [tiles][NJ][2][Cout] = sum, sum of squares of round(y * 2^16) over
+        the rows of a 128-position tile that belong to one image"""
+        B, H, W, Cout, ks = op.B, op.H, op.W, op.Cout, op.i0
+        pimg, nj, ntiles = self._tile_geometry(B, H, W, ks)
+        st = self.get(op.dst2, ntiles * nj * 2 * Cout, torch.int64).view(ntiles, nj, 2, Cout)
+        st.zero_()
+        xi = torch.round(y.double() * 65536.0).clamp(-(1 << 28), 1 << 28).to(torch.int64)
+        yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        r = ((yy + 1) * (W + 1) + xx + 1) if ks == 3 else (yy * W + xx)
+        for b in range(B):
+            q = (b * pimg + r).reshape(-1)
+            t = q // 128
+            jj = b - torch.clamp((t * 128) // pimg, max=B - 1)
+            v = xi[b].reshape(H * W, Cout)
+            st[:, :, 0].index_put_((t, jj), v, accumulate=True)
+            st[:, :, 1].index_put_((t, jj), v * v, accumulate=True)
+
     # -- ops ----------------------------------------------------------------------------------------
     def exec(self, op):
         k = op.kind
@@ -140,11 +165,25 @@ class Interpreter:
                 out[:, c, :, 1] = (seg * seg).sum(1)
         elif k == lib.OP_GN_FINALIZE:
             C, nchunk, cg = op.C0 + op.C1, op.i0, op.i1
-            part = self.get(op.src0, B * nchunk * op.C0 * 2, torch.float64).view(B, nchunk, op.C0, 2)
+
+            def chan_sums(ptr, Cs, kind):
+                """per (b, channel) sum / sum of squares as float64 [B, Cs, 2]"""
+                if kind == 0:
+                    return self.get(ptr, B * nchunk * Cs * 2, torch.float64).view(B, nchunk, Cs, 2).sum(1)
+                pimg, nj, ntiles = self._tile_geometry(B, H, W, kind)
+                st = self.get(ptr, ntiles * nj * 2 * Cs, torch.int64).view(ntiles, nj, 2, Cs)
+                out = torch.zeros(B, Cs, 2, dtype=torch.float64)
+                for b in range(B):
+                    for t in range((b * pimg) // 128, ((b + 1) * pimg - 1) // 128 + 1):
+                        jj = b - min(B - 1, (t * 128) // pimg)
+                        out[b, :, 0] += st[t, jj, 0].double() / 65536.0
+                        out[b, :, 1] += st[t, jj, 1].double() / 4294967296.0
+                return out
+
+            part = chan_sums(op.src0, op.C0, op.i4)
             if op.C1 > 0:
-                p1 = self.get(op.src1, B * nchunk * op.C1 * 2, torch.float64).view(B, nchunk, op.C1, 2)
-                part = torch.cat([part, p1], dim=2)
-            s = part.sum(1).view(B, C // cg, cg, 2).sum(2)          # [B, G, 2]
+                part = torch.cat([part, chan_sums(op.src1, op.C1, op.i5)], dim=1)
+            s = part.view(B, C // cg, cg, 2).sum(2)                 # [B, G, 2]
             cnt = H * W * cg
             mean = s[..., 0] / cnt
             var = (s[..., 1] / cnt - mean * mean).clamp_min(0)
@@ -166,6 +205,8 @@ class Interpreter:
                     S = self.get(op.aux1, C)[None].expand(B, C)
             tab = torch.stack([mean_c, rstd_c, G, S], dim=2)
             self.get(op.dst, B * C * 4).copy_(tab.reshape(-1))
+            if op.dst2:                                             # planar table read by CONV_UMMA2
+                self.get(op.dst2, B * 3 * C).copy_(torch.stack([mean_c, rstd_c * G, S], dim=1).reshape(-1))
         elif k == lib.OP_APPLY:
             Hin, Win = H, W
             if op.flags & lib.F_DOWN:
@@ -188,22 +229,26 @@ class Interpreter:
                     n = silu(n)
                 x = n
             self._fir_store(op, x.permute(0, 3, 1, 2), op.dst, B, C, H, W, Hin, Win)
-        elif k in (lib.OP_CONV_SIMT, lib.OP_CONV_UMMA):
+        elif k in (lib.OP_CONV_SIMT, lib.OP_CONV_UMMA, lib.OP_CONV_UMMA2):
             x = self._src(op, H, W)
             C = op.C0 + op.C1
-            if k == lib.OP_CONV_UMMA:
+            if k in (lib.OP_CONV_UMMA, lib.OP_CONV_UMMA2):
                 OP = op.Cout
                 scale, wscale = float(op.f0), float(op.f1)
                 if op.aux1:
-                    tab = self.get(op.aux1, B * C * 4).view(B, 1, 1, C, 4)
-                    x = ((x - tab[..., 0]) * tab[..., 1]) * tab[..., 2] + tab[..., 3]
+                    if k == lib.OP_CONV_UMMA2:                      # planar [B][3][C]: mean | rstd*G | S
+                        t3 = self.get(op.aux1, B * 3 * C).view(B, 3, 1, 1, C)
+                        x = (x - t3[:, 0]) * t3[:, 1] + t3[:, 2]
+                    else:
+                        tab = self.get(op.aux1, B * C * 4).view(B, 1, 1, C, 4)
+                        x = ((x - tab[..., 0]) * tab[..., 1]) * tab[..., 2] + tab[..., 3]
                     if op.flags & lib.F_ACT_IN:
                         x = silu(x)
             else:
                 OP = op.i1
                 scale, wscale = float(op.f0), 1.0
             y = self._conv(op, x, OP) * wscale
-            if k == lib.OP_CONV_UMMA and op.src2:
+            if k in (lib.OP_CONV_UMMA, lib.OP_CONV_UMMA2) and op.src2:
                 # second K-segment: raw 1x1 conv of (src2|src3); its [1][C2+C3][Cout] weights follow the main ones
                 Hs = H
                 a2 = self.get(op.src2, B * Hs * W * op.C2).view(B, Hs, W, op.C2)
@@ -221,6 +266,8 @@ class Interpreter:
             if op.flags & lib.F_ACT_OUT:
                 y = silu(y)
             self.get(op.dst, y.numel()).copy_(y.reshape(-1))
+            if k == lib.OP_CONV_UMMA2 and op.dst2:
+                self._tile_stats(op, y.reshape(B, H, W, op.Cout))
         elif k == lib.OP_CONV_SMALLN:
             x = self.get(op.src0, B * H * W * op.C0).view(B, H, W, op.C0)
             if op.aux0:
