@@ -73,6 +73,9 @@ struct C2Args {
   long long Qtot;
   int NT, KB, HP, halo0, NB, SA, R, tiles_n, nunits, tmem_cols, NJ;
   int act_in, act_out, split;
+  int dbgf;                     // bring-up switches (tools/conv2_check.py): 1 producers skip copies + transform, 2 epilogue skips
+                                // its loads / stores, 4 weight stages are not reloaded, 8 leader ignores the peer's stage barriers, 16 no slab
+                                // pipeline at all (producers idle, MMA does not wait for slabs), 32 no weight pipeline -- garbage results, timing only
   float wscale, oscale;
   uint32_t off_img, off_raw, off_b, off_pad, off_row, off_stat, off_bias, off_bar;
   uint32_t a_plane, raw_stage, b_stage;
@@ -135,7 +138,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
   const int per_unit = a.nKB0 * taps + (a.nKB - a.nKB0);       // weight stages per unit
 
   if (tid == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(A_FULL(i), NPROD); mbar_init(A_EMPTY(i), 1); mbar_init(PA_FULL(i), 1); }
+    for (int i = 0; i < SA; ++i) { mbar_init(A_FULL(i), NPROD / 32); mbar_init(A_EMPTY(i), 1); mbar_init(PA_FULL(i), 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); mbar_init(PB_FULL(i), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 256); }
     fence_barrier_init();
@@ -182,7 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
 
     int i_unit = 0, i_kb = 0;        // issue stream position
     int t_unit = 0, t_kb = 0;        // transform stream position
-    for (int it = 0; it < total + Rm1; ++it) {
+    for (int it = 0; it < ((a.dbgf & 16) ? 0 : total + Rm1); ++it) {
       // ---- issue the copies of job `it` (K-block i_kb of unit i_unit) into raw stage it % R ----
       if (it < total) {
         const int par = i_unit & 1;
@@ -206,7 +209,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
         const int hlo = seg1 ? a.halo0 : 0, hhi = seg1 ? a.halo0 + MT : a.HP;
         const uint32_t rst = raw0 + (uint32_t)(it % a.R) * a.raw_stage;
         const float* sj = src + cc0 + j * 4;
-        for (int h = hrow; h < hhi; h += RPP) {
+        for (int h = hrow; h < hhi && !(a.dbgf & 1); h += RPP) {
           if (h < hlo) continue;
           const int pix = rowinfo[par * a.HP + h].x;
           const float* p = pix >= 0 ? sj + (long long)pix * cs : src;
@@ -221,7 +224,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
       if (Rm1 == 1) wait_copies<1>(); else if (Rm1 == 2) wait_copies<2>(); else wait_copies<3>();
       const int st = gt % SA;
       DBG_T(tp);
-      mbar_wait(A_EMPTY(st), ((gt / SA) & 1) ^ 1);
+      // one lane per warp polls (32 lanes spinning on the same mbarrier steal shared-memory cycles from the
+      // tensor core's operand reads); __syncwarp orders the other lanes behind lane 0's acquire
+      if (lane == 0) mbar_wait(A_EMPTY(st), ((gt / SA) & 1) ^ 1);
+      __syncwarp();
       DBG_ADD(1, tp, tid == 0);
       const int par = t_unit & 1;
       const bool seg1 = t_kb >= a.nKB0;
@@ -231,8 +237,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
       const uint32_t hi_base = img0 + (uint32_t)st * 2u * a.a_plane, lo_base = hi_base + a.a_plane;
       const uint32_t img_off = (uint32_t)(j >> 1) * (uint32_t)a.HP * 16u + (uint32_t)(j & 1) * 8u;
       const float* tabc = a.tab3 + t_kb * a.KB + j * 4;
-#pragma unroll 2
-      for (int h = hrow; h < hhi; h += RPP) {
+      // (mean, rstd*G, S) of this thread's 4 channels for the image of the current row: a slab touches one or two
+      // images on the large maps, so the three L1 loads are paid once per K-block, not once per row
+      float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), tg = tm, ts = tm;
+      int tb_img = -1;
+#pragma unroll 4
+      for (int h = hrow; h < hhi && !(a.dbgf & 1); h += RPP) {
         if (h < hlo) continue;
         const int2 info = rowinfo[par * a.HP + h];
         float4 x;
@@ -243,12 +253,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
         if (info.x >= 0) {
           float v[4] = {x.x, x.y, x.z, x.w};
           if (norm) {
-            const float* tb = tabc + (long long)info.y * 3 * Cin;
-            const float4 m = __ldg(reinterpret_cast<const float4*>(tb));
-            const float4 g = __ldg(reinterpret_cast<const float4*>(tb + Cin));
-            const float4 s = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
-            v[0] = fmaf(v[0] - m.x, g.x, s.x); v[1] = fmaf(v[1] - m.y, g.y, s.y);
-            v[2] = fmaf(v[2] - m.z, g.z, s.z); v[3] = fmaf(v[3] - m.w, g.w, s.w);
+            if (info.y != tb_img) {
+              const float* tb = tabc + (long long)info.y * 3 * Cin;
+              tm = __ldg(reinterpret_cast<const float4*>(tb));
+              tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
+              ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
+              tb_img = info.y;
+            }
+            v[0] = fmaf(v[0] - tm.x, tg.x, ts.x); v[1] = fmaf(v[1] - tm.y, tg.y, ts.y);
+            v[2] = fmaf(v[2] - tm.z, tg.z, ts.z); v[3] = fmaf(v[3] - tm.w, tg.w, ts.w);
             if (a.act_in) silu_fast4(v);
           }
           split2_sat(v[0], v[1], h0, l0);
@@ -259,8 +272,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
         asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_base + off), "r"(l0), "r"(l1) : "memory");
       }
       DBG_ADD(3, tp, tid == 0);
-      fence_proxy_async_all();            // generic-proxy stores -> visible to the tensor-core (async) proxy
-      mbar_arrive(A_FULL(st));
+      fence_proxy_async();                // generic-proxy smem stores -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(A_FULL(st));          // one arrival per producer warp
       DBG_ADD(4, tp, tid == 0);
       if (++t_kb == a.nKB) { t_kb = 0; ++t_unit; }
     }
@@ -269,11 +283,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
     if (elect_one()) {
       const uint32_t b0 = sbase + a.off_b;
       int st = 0, ph = 1;
-      for (int iu = 0; iu < my_units; ++iu) {
+      for (int iu = 0; iu < ((a.dbgf & 32) ? 0 : my_units); ++iu) {
         const int u = cid + iu * ncl;
         const uint8_t* wsrc = a.wpk + ((size_t)(u % a.tiles_n) * per_unit * 2 + rank) * a.b_stage;
         for (int i = 0; i < per_unit; ++i) {
           mbar_wait(B_EMPTY(st), ph);
+          if (a.dbgf & 4) { mbar_arrive(B_FULL(st)); if (++st == NB) { st = 0; ph ^= 1; } continue; }
           mbar_arrive_expect_tx(B_FULL(st), a.b_stage);
           bulk_g2s(b0 + (uint32_t)st * a.b_stage, wsrc + (size_t)i * 2 * a.b_stage, a.b_stage, B_FULL(st));
           if (++st == NB) { st = 0; ph ^= 1; }
@@ -306,19 +321,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
             const int st = g % SA;
             const uint32_t aph = (uint32_t)((g / SA) & 1);
             DBG_ADD(8, tm, true);
-            mbar_wait(A_FULL(st), aph);
-            mbar_wait_cluster(PA_FULL(st), aph);
+            if (!(a.dbgf & 16)) {
+              mbar_wait(A_FULL(st), aph);
+              if (!(a.dbgf & 8)) mbar_wait_cluster(PA_FULL(st), aph);
+            }
             DBG_ADD(6, tm, true);
-            tc_fence_after();
+            // no tcgen05.fence here: the slab was written through the generic proxy and published with
+            // fence.proxy.async + mbarrier release/acquire; a tcgen05.fence::after_thread_sync per stage drained
+            // the MMA pipeline (~500 cycles per weight stage in round 1 and in the first version of this kernel)
             const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
             const bool main = kb < a.nKB0;
             const int ntap = main ? taps : 1;
             for (int tap = 0; tap < ntap; ++tap) {
               DBG_ADD(8, tm, true);
-              mbar_wait(B_FULL(bst), bph);
-              mbar_wait_cluster(PB_FULL(bst), bph);
+              if (!(a.dbgf & 32)) {
+                mbar_wait(B_FULL(bst), bph);
+                if (!(a.dbgf & 8)) mbar_wait_cluster(PB_FULL(bst), bph);
+              }
               DBG_ADD(7, tm, true);
-              tc_fence_after();
               const int shift = (a.ks == 3 && main) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
               const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
               const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
@@ -348,12 +368,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
         for (int iu = 0; iu < my_units; ++iu) {
           for (int kb = 0; kb < a.nKB; ++kb, ++g) {
             const int st = g % SA;
-            mbar_wait(A_FULL(st), (uint32_t)((g / SA) & 1));
-            mbar_arrive_remote(mapa_u32(PA_FULL(st), 0));
+            if (!(a.dbgf & 16)) {
+              mbar_wait(A_FULL(st), (uint32_t)((g / SA) & 1));
+              mbar_arrive_remote(mapa_u32(PA_FULL(st), 0));
+            }
             const int ntap = (kb < a.nKB0) ? taps : 1;
             for (int tap = 0; tap < ntap; ++tap) {
-              mbar_wait(B_FULL(bst), bph);
-              mbar_arrive_remote(mapa_u32(PB_FULL(bst), 0));
+              if (!(a.dbgf & 32)) {
+                mbar_wait(B_FULL(bst), bph);
+                mbar_arrive_remote(mapa_u32(PB_FULL(bst), 0));
+              }
               if (++bst == NB) { bst = 0; bph ^= 1; }
             }
           }
@@ -407,10 +431,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
       };
       if (a.NT >= 32) res_fetch(0);
       DBG_T(te);
-      mbar_wait(ACC_FULL(set), (uint32_t)((iu >> 1) & 1));
+      if (lane == 0) mbar_wait(ACC_FULL(set), (uint32_t)((iu >> 1) & 1));
+      __syncwarp();
       DBG_ADD(9, te, tid == W_EPI * 32);
       tc_fence_after();
       const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(set * a.NT);
+      if (a.dbgf & 2) {
+        tc_fence_before();
+        if (rank == 0) mbar_arrive(ACC_EMPTY(set)); else mbar_arrive_remote(acc_empty_leader + 8u * set);
+        continue;
+      }
       for (int blk = 0; blk < nblk; ++blk) {
         const int cb = blk * 32;
         const int w = min(32, a.NT - cb);
@@ -727,6 +757,7 @@ int launch_conv_umma2(const McvdOp& op, cudaStream_t s) {
   a.split = (op.i3 >= 1 && op.i3 <= 3) ? op.i3 : 3;
   if (op.i3 == 4) a.split = 0;                     // single fp16 MMA (experiments only)
   a.wscale = op.f1; a.oscale = op.f0;
+  a.dbgf = op.i7;
   a.tiles_n = op.Cout / a.NT;
   const long long pairs_m = (a.Qtot + 2 * MT - 1) / (2 * MT);
   a.nunits = (int)(pairs_m * a.tiles_n);

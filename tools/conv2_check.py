@@ -4,7 +4,8 @@ with CUDA events, with the in-kernel cycle counters.
 
 usage: conv2_check.py B H C0 C1 Cout ks [flags]     flags: t=norm table+SiLU, r=residual, s<C2>[,<C3>]=fused 1x1
                                                     shortcut, g=epilogue GroupNorm statistics, n<NT>=n tile,
-                                                    m<k>=split mode, q=skip the CPU reference (compare with v1)
+                                                    m<k>=split mode, q=skip the CPU reference (compare with v1),
+                                                    d<bits>=timing switches (1 no producer work, 2 no epilogue, 4 no weight reloads)
 """
 import math
 import os
@@ -26,6 +27,7 @@ quick = "q" in flags
 C2 = C3 = 0
 NT = max(d for d in range(16, 257, 16) if Cout % d == 0)
 split = 3
+dbgf = 0
 for f in flags:
     if f.startswith("s"):
         cs = [int(v) for v in f[1:].split(",")]
@@ -34,6 +36,8 @@ for f in flags:
         NT = int(f[1:])
     if f.startswith("m"):
         split = int(f[1:])
+    if f.startswith("d"):
+        dbgf = int(f[1:])
 dev = "cuda:0"
 Cin, Cs = C0 + C1, C2 + C3
 g = torch.Generator().manual_seed(1)
@@ -82,6 +86,7 @@ if Cs:
     o.src2, o.C2 = y0d.data_ptr(), C2
     if C3: o.src3, o.C3 = y1d.data_ptr(), C3
 if use_stats: o.dst2 = stats.data_ptr()
+o.i7 = dbgf
 arr = lib.make_ops([o])
 lib.run_program(arr, 1, stream)
 torch.cuda.synchronize()
