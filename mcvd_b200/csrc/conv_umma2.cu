@@ -14,27 +14,31 @@
 // every image being shared zero padding, so a 3x3 tap is a constant flat offset and all nine taps are shifted
 // views (descriptor start + offset*16 B) of ONE halo slab  [k-chunk of 8 halfs][position][16 B]  per K-block.
 //
-// What changed against conv_umma.cu (round 1), and why (profiles/r2_timing_v1_round1_kernel.txt):
-//   * CTA pairs.  A unit of work is 256 positions x NT output channels.  CTA r of the pair stages the slab of
-//     ITS 128 positions and loads ITS half (NT/2 columns) of the weight tile; one tcgen05.mma.cta_group::2
-//     issued by the leader covers both.  Per instruction each SM now reads 4 KB of A + NT*16 B of B from its
-//     shared memory instead of 4 KB + NT*32 B for half the work: the A-operand read floor of round 1
-//     (64 + N/4 cycles per M128 instruction) becomes max(N/2, 64 + N/8) per M256, and the weight traffic
-//     from L2 per SM halves.
-//   * Producers: 9 warps, unit = (slab row, 16-byte piece) so global reads are whole 128-byte lines and
-//     shared-memory accesses are conflict-free; the fp32 rows arrive through a cp.async ring (R stages,
-//     prefetch distance R-1 K-blocks, zero-fill for padding rows) instead of registers, every thread reads
-//     back only what it copied itself (no producer-side barriers), and the norm table comes from L1.
-//     Round 1 ran the 1x1 convs with ONE producer warp per SM sub-partition (2.5k cycles per K-block).
-//   * The fused 1x1 shortcut segment stages only the 128 centre rows (no halo).
-//   * Epilogue: optional per-(image, channel) sum / sum of squares of the stored output, accumulated
-//     EXACTLY in 64-bit fixed point (x * 2^16 rounded to an integer), so the result does not depend on how
-//     the rows of an image fall into tiles, warps or GPUs (bit-exact clip sharding is preserved) -- this
-//     replaces the k_gn_partial pass (one extra read of every activation).
+// What the measurements of round 2 said (profiles/r2_mma_rate_microbench.txt, r2_conv2_isolation.txt) and what
+// this kernel does about it:
+//   * Back-to-back tcgen05.mma run at the tensor floor (N/2 cycles per 128 rows per SM for N >= 96 in cta_group::2,
+//     any operand layout, shifted descriptors included): the round-1 "A-operand read floor" does not exist.  What
+//     cost round 1 (and the first version of this file) a factor 2-3 was the pipeline AROUND the MMAs.
+//   * Weights.  Re-streaming the weight tile for every 128 positions needs ~20 B/clk per SM = 5.8 TB/s from L2
+//     at full tensor speed; measured, the loads alone cost +50 % (L2 delivers these hot lines at ~2.8 TB/s).  So a
+//     unit of work is J (= 2..4) position tiles per CTA against one n tile: loop order K-block -> tap -> tile, the
+//     J slabs of a K-block are resident together and every weight stage is used J times.  The pair splits the n
+//     tile (cta_group::2: each CTA stages NT/2 columns), so per SM the weight bytes per position drop 2J-fold
+//     against a single-CTA, single-tile schedule.
+//   * No forwarding hops.  Weight stages arrive by TMA (cp.async.bulk.tensor ... .cta_group::2) that signals the
+//     LEADER's mbarrier from both CTAs; the peer's producer warps arrive on the leader's slab barrier directly
+//     (one remote arrive per warp); tcgen05.commit multicasts "stage free" to both CTAs.
+//   * One arrive / one polling lane per warp everywhere (128 remote arrives per tile on the accumulator barrier
+//     cost ~8k cycles per tile before).
+//   * Producers: 9 warps, unit = (slab row, 16-byte piece): whole 128-byte lines from global, conflict-free shared
+//     memory, fp32 rows staged through a cp.async ring (zero-fill for padding), thread-private (no barriers).
+//   * Epilogue: 8 warps (two groups of four TMEM-lane quadrants, one position tile each), smem-transposed
+//     128-byte-line stores, optional exact integer GroupNorm partial sums of the stored output (fixed point
+//     2^-16, order-independent => bit-exact under clip sharding), which replaces the k_gn_partial pass.
 //
-// Warp roles (480 threads, one CTA per SM, clusters of 2):
-//   warps 0-8   producers   warp 9 weight loader (cp.async.bulk)   warp 10 MMA issuer (leader) / barrier
-//   forwarder (peer)        warps 11-14 epilogue (TMEM lane quadrants 3,0,1,2)
+// Warp roles (608 threads, one CTA per SM, clusters of 2):
+//   warps 0-8 producers | 9 weight loader (TMA) | 10 MMA issuer (leader CTA only) | 11-18 epilogue
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "mcvd_common.cuh"
@@ -47,13 +51,15 @@ namespace {
 using namespace ptx;
 
 constexpr int NPROD = 288;
+constexpr int NPW = NPROD / 32;
 constexpr int W_LOAD = 9;
 constexpr int W_MMA = 10;
 constexpr int W_EPI = 11;
-constexpr int NTHREADS = 480;
-constexpr int MT = 128;                 // positions per CTA and unit
+constexpr int NEPI_W = 8;
+constexpr int NTHREADS = (W_EPI + NEPI_W) * 32;      // 608
+constexpr int MT = 128;                 // positions per CTA and tile
+constexpr int JMAX = 4;                 // position tiles per unit (accumulators per TMEM set)
 constexpr float STAT_SCALE = 65536.0f;  // fixed-point scale of the epilogue statistics
-constexpr int STAT_CLAMP = 1 << 28;
 
 struct C2Args {
   const float* s0;
@@ -62,7 +68,6 @@ struct C2Args {
   const float* s3;
   int C0, C1, C2, C3;
   int nKB0, nKB;
-  const uint8_t* wpk;
   const float* bias;
   const float* res;
   const float* tab3;            // [B][3][C0+C1]: mean | rstd*G | S   (null: raw input)
@@ -71,29 +76,25 @@ struct C2Args {
   long long* dbg;
   int B, H, W, Cout, ks, Wp, Pimg, HW;
   long long Qtot;
-  int NT, KB, HP, halo0, NB, SA, R, tiles_n, nunits, tmem_cols, NJ;
+  int NT, KB, HP, halo0, NB, SA, R, J, nsets, tiles_n, PT, njobs, tmem_cols, NJ;
   int act_in, act_out, split;
-  int dbgf;                     // bring-up switches (tools/conv2_check.py): 1 producers skip copies + transform, 2 epilogue skips
-                                // its loads / stores, 4 weight stages are not reloaded, 8 leader ignores the peer's stage barriers, 16 no slab
-                                // pipeline at all (producers idle, MMA does not wait for slabs), 32 no weight pipeline -- garbage results, timing only
+  int dbgf;                     // timing switches (tools/conv2_check.py): 1 producers skip copies + transform, 2 the
+                                // epilogue skips loads / stores, 4 weight stages are not reloaded -- garbage results
   float wscale, oscale;
   uint32_t off_img, off_raw, off_b, off_pad, off_row, off_stat, off_bias, off_bar;
-  uint32_t a_plane, raw_stage, b_stage;
+  uint32_t a_plane, raw_stage, b_stage, b_rows;      // b_rows = 512-byte rows of the weight tensor map per stage
 };
 
-// flat position -> pixel index (b*H + y)*W + x or -1 (padding / out of range); b_out = image
-__device__ __forceinline__ int decode_pos(const C2Args& a, long long q, int& b_out) {
-  b_out = 0;
+// flat position -> pixel index (b*H + y)*W + x or -1 (padding / out of range)
+__device__ __forceinline__ int decode_pos(const C2Args& a, long long q) {
   if (q < 0 || q >= a.Qtot) return -1;
   const int b = (int)(q / a.Pimg);
   const int r = (int)(q - (long long)b * a.Pimg);
   const int rr = r / a.Wp, cc = r - rr * a.Wp;
-  b_out = b;
   if (a.ks == 3) {
-    if (rr == 0 || cc == 0 || rr > a.H) return -1;
+    if (rr == 0 || cc == 0) return -1;
     return (b * a.H + (rr - 1)) * a.W + (cc - 1);
   }
-  if (rr >= a.H) return -1;
   return (b * a.H + rr) * a.W + cc;
 }
 
@@ -114,10 +115,34 @@ __device__ __forceinline__ float4 ld_nc_na(const float* p) {      // read-only, 
   return v;
 }
 
-template <int PEND>
-__device__ __forceinline__ void wait_copies() { cp_async_wait<PEND>(); }
+// TMA: one weight stage (b_rows x 512 B) -> this CTA's shared memory, complete_tx on the LEADER's mbarrier
+__device__ __forceinline__ void tma_load_stage(uint32_t dst, const CUtensorMap* tmap, int row, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(0), "r"(row)
+      : "memory");
+}
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_umma2(const __grid_constant__ C2Args a) {
+// the units of a cluster: consecutive (n tile, position-pair tile) jobs [i, end), grouped J at a time inside an n tile
+struct Units {
+  int i, end, PT, J;
+  __device__ Units(const C2Args& a, int cid, int ncl) {
+    i = (int)((long long)cid * a.njobs / ncl);
+    end = (int)((long long)(cid + 1) * a.njobs / ncl);
+    PT = a.PT; J = a.J;
+  }
+  __device__ bool next(int& nt, int& pt0, int& cnt) {
+    if (i >= end) return false;
+    nt = i / PT; pt0 = i - nt * PT;
+    cnt = min(J, min(end - i, PT - pt0));
+    i += cnt;
+    return true;
+  }
+};
+
+template <int KSTEPS>      // k16 steps per K-block: 1 (KB = 16) or 2 (KB = 32)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -125,27 +150,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + a.off_bar;
   const int SA = a.SA, NB = a.NB;
-  auto A_FULL = [&](int i) { return bar0 + 8u * i; };
-  auto A_EMPTY = [&](int i) { return bar0 + 8u * (SA + i); };
-  auto PA_FULL = [&](int i) { return bar0 + 8u * (2 * SA + i); };
-  auto B_FULL = [&](int i) { return bar0 + 8u * (3 * SA + i); };
-  auto B_EMPTY = [&](int i) { return bar0 + 8u * (3 * SA + NB + i); };
-  auto PB_FULL = [&](int i) { return bar0 + 8u * (3 * SA + 2 * NB + i); };
-  auto ACC_FULL = [&](int i) { return bar0 + 8u * (3 * SA + 3 * NB + i); };
-  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (3 * SA + 3 * NB + 2 + i); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.off_bar + 8 * (3 * SA + 3 * NB + 4));
+  // barriers (same offsets in both CTAs; the *_FULL ones are only waited on in the leader)
+  auto A_FULL = [&](int i) { return bar0 + 8u * i; };                       // 2 * NPW warp arrivals (local + peer)
+  auto A_EMPTY = [&](int i) { return bar0 + 8u * (SA + i); };               // tcgen05.commit, multicast
+  auto B_FULL = [&](int i) { return bar0 + 8u * (2 * SA + i); };            // expect_tx (leader) + TMA bytes of both CTAs
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (2 * SA + NB + i); };      // tcgen05.commit, multicast
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * SA + 2 * NB + i); };             // [set*JMAX + j], commit mc
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * SA + 2 * NB + 2 * JMAX + i); }; // 8 warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.off_bar + 8 * (2 * SA + 2 * NB + 4 * JMAX));
   const int taps = a.ks * a.ks;
-  const int per_unit = a.nKB0 * taps + (a.nKB - a.nKB0);       // weight stages per unit
 
   if (tid == 0) {
-    for (int i = 0; i < SA; ++i) { mbar_init(A_FULL(i), NPROD / 32); mbar_init(A_EMPTY(i), 1); mbar_init(PA_FULL(i), 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); mbar_init(PB_FULL(i), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 256); }
+    for (int i = 0; i < SA; ++i) { mbar_init(A_FULL(i), 2 * NPW); mbar_init(A_EMPTY(i), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
+    for (int i = 0; i < 2 * JMAX; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 8); }
     fence_barrier_init();
   }
   if (a.stats) {
     unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + a.off_stat);
-    for (int i = tid; i < a.NJ * 2 * a.NT; i += NTHREADS) st[i] = 0ull;
+    for (int i = tid; i < 2 * a.NJ * 2 * a.NT; i += NTHREADS) st[i] = 0ull;
   }
   if (warp == W_MMA) tmem_alloc2(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
@@ -158,19 +181,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
 #define DBG_T(var) long long var = dbg ? clock64() : 0
 #define DBG_ADD(slot, since, cond) do { if (dbg && (cond)) { long long t__ = clock64(); dbg[slot] += t__ - since; since = t__; } } while (0)
 
-  const int my_units = (a.nunits - cid + ncl - 1) / ncl;        // units cid, cid + ncl, ...
-
   if (warp < W_LOAD) {
     // =============================== producers ===============================
+    // job = (unit, K-block kb, tile j): the slab of position tile pt0+j for channels [kb*KB, +KB), in the order the
+    // MMA warp consumes them (unit -> kb -> j).  Copies of job g go to raw stage g % R, its fp16 image to image
+    // stage g % SA; the copies run R-1 jobs ahead of the transform.
     const int pj_shift = (a.KB == 32) ? 3 : 2;                 // 16-byte pieces per slab row: 8 or 4
     const int PJ = 1 << pj_shift;
-    const int j = tid & (PJ - 1);
+    const int j16 = tid & (PJ - 1);
     const int hrow = tid >> pj_shift;
     const int RPP = NPROD >> pj_shift;                         // rows per pass: 36 or 72
     const int Cin = a.C0 + a.C1;
     const uint32_t raw0 = sbase + a.off_raw, img0 = sbase + a.off_img;
-    int2* rowinfo = reinterpret_cast<int2*>(smem + a.off_row);   // [2][HP] (pix, image)
-    const int total = my_units * a.nKB;
+    int* rowinfo = reinterpret_cast<int*>(smem + a.off_row);     // [2 (unit parity)][J][HP] pixel index or -1
+    const uint32_t a_full_leader = mapa_u32(A_FULL(0), 0);
     const int Rm1 = a.R - 1;
 
     auto src_of = [&](int kb, const float*& src, int& cs, int& cc0) {
@@ -183,114 +207,144 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
       }
     };
 
-    int i_unit = 0, i_kb = 0;        // issue stream position
-    int t_unit = 0, t_kb = 0;        // transform stream position
-    for (int it = 0; it < ((a.dbgf & 16) ? 0 : total + Rm1); ++it) {
-      // ---- issue the copies of job `it` (K-block i_kb of unit i_unit) into raw stage it % R ----
+    int total = 0;
+    {
+      Units u0(a, cid, ncl);
+      int n_, p_, c_;
+      while (u0.next(n_, p_, c_)) total += c_ * a.nKB;
+    }
+    // two cursors over the same job sequence
+    Units ui(a, cid, ncl), ut(a, cid, ncl);
+    int i_nt = 0, i_pt0 = 0, i_cnt = 0, i_kb = 0, i_j = 0, i_par = 0;
+    int t_nt = 0, t_pt0 = 0, t_cnt = 0, t_kb = 0, t_j = 0, t_par = 0;
+    ui.next(i_nt, i_pt0, i_cnt);
+    ut.next(t_nt, t_pt0, t_cnt);
+    bool i_new = true;                                          // the issue cursor entered a new unit
+    for (int it = 0; it < total + Rm1; ++it) {
+      // ---- issue the copies of job `it` into raw stage it % R ----
       if (it < total) {
-        const int par = i_unit & 1;
-        if (i_kb == 0) {
-          // slab row -> pixel table of this unit (the transform stream may still read the other buffer)
+        if (i_new) {
+          // slab row -> pixel table of the unit's tiles (the transform cursor may still read the other buffer: it is
+          // at most R-1 <= nKB jobs, i.e. at most one unit, behind)
           named_bar_sync(1, NPROD);
-          const int u = cid + i_unit * ncl;
-          const long long p0 = (long long)(u / a.tiles_n) * (2 * MT) + (long long)rank * MT - a.halo0;
-          for (int h = tid; h < a.HP; h += NPROD) {
-            int b;
-            const int pix = decode_pos(a, p0 + h, b);
-            rowinfo[par * a.HP + h] = make_int2(pix, b);
+          for (int x = tid; x < i_cnt * a.HP; x += NPROD) {
+            const int jj = x / a.HP, h = x - jj * a.HP;
+            const long long p0 = (long long)(i_pt0 + jj) * (2 * MT) + (long long)rank * MT - a.halo0;
+            rowinfo[(i_par * a.J + jj) * a.HP + h] = decode_pos(a, p0 + h);
           }
           named_bar_sync(1, NPROD);
+          i_new = false;
         }
         const float* src; int cs, cc0;
         src_of(i_kb, src, cs, cc0);
-        // slab row h always belongs to thread group h % RPP (whatever the segment), so a raw-ring slot is
-        // only ever touched by one thread and needs no barrier; the 1x1 shortcut segment stages the centre rows only
+        // slab row h always belongs to thread group h % RPP (whatever the segment), so a raw-ring slot is only ever
+        // touched by one thread and needs no barrier; the 1x1 shortcut segment stages the centre rows only
         const bool seg1 = i_kb >= a.nKB0;
         const int hlo = seg1 ? a.halo0 : 0, hhi = seg1 ? a.halo0 + MT : a.HP;
         const uint32_t rst = raw0 + (uint32_t)(it % a.R) * a.raw_stage;
-        const float* sj = src + cc0 + j * 4;
-        for (int h = hrow; h < hhi && !(a.dbgf & 1); h += RPP) {
-          if (h < hlo) continue;
-          const int pix = rowinfo[par * a.HP + h].x;
-          const float* p = pix >= 0 ? sj + (long long)pix * cs : src;
-          cp_async16(rst + (uint32_t)((h << pj_shift) + j) * 16u, p, pix >= 0 ? 16u : 0u);
+        const float* sj = src + cc0 + j16 * 4;
+        const int* ri = rowinfo + (i_par * a.J + i_j) * a.HP;
+        if (!(a.dbgf & 1)) {
+          for (int h = hrow; h < hhi; h += RPP) {
+            if (h < hlo) continue;
+            const int pix = ri[h];
+            const float* p = pix >= 0 ? sj + (long long)pix * cs : src;
+            cp_async16(rst + (uint32_t)((h << pj_shift) + j16) * 16u, p, pix >= 0 ? 16u : 0u);
+          }
         }
-        if (++i_kb == a.nKB) { i_kb = 0; ++i_unit; }
+        if (++i_j == i_cnt) {
+          i_j = 0;
+          if (++i_kb == a.nKB) { i_kb = 0; ui.next(i_nt, i_pt0, i_cnt); i_par ^= 1; i_new = true; }
+        }
       }
       cp_async_commit();
       // ---- transform job it - (R-1) ----
       const int gt = it - Rm1;
       if (gt < 0) continue;
-      if (Rm1 == 1) wait_copies<1>(); else if (Rm1 == 2) wait_copies<2>(); else wait_copies<3>();
+      if (Rm1 == 1) cp_async_wait<1>(); else if (Rm1 == 2) cp_async_wait<2>(); else cp_async_wait<3>();
       const int st = gt % SA;
       DBG_T(tp);
-      // one lane per warp polls (32 lanes spinning on the same mbarrier steal shared-memory cycles from the
-      // tensor core's operand reads); __syncwarp orders the other lanes behind lane 0's acquire
-      if (lane == 0) mbar_wait(A_EMPTY(st), ((gt / SA) & 1) ^ 1);
+      // one lane per warp polls; __syncwarp orders the other lanes behind lane 0's acquire
+      if (lane == 0) { if (a.dbgf & 8) mbar_wait(A_EMPTY(st), ((gt / SA) & 1) ^ 1); else mbar_wait_parked(A_EMPTY(st), ((gt / SA) & 1) ^ 1); }
       __syncwarp();
       DBG_ADD(1, tp, tid == 0);
-      const int par = t_unit & 1;
       const bool seg1 = t_kb >= a.nKB0;
       const bool norm = a.tab3 != nullptr && !seg1;
       const int hlo = seg1 ? a.halo0 : 0, hhi = seg1 ? a.halo0 + MT : a.HP;
       const uint32_t rst = raw0 + (uint32_t)(gt % a.R) * a.raw_stage;
       const uint32_t hi_base = img0 + (uint32_t)st * 2u * a.a_plane, lo_base = hi_base + a.a_plane;
-      const uint32_t img_off = (uint32_t)(j >> 1) * (uint32_t)a.HP * 16u + (uint32_t)(j & 1) * 8u;
-      const float* tabc = a.tab3 + t_kb * a.KB + j * 4;
+      const uint32_t img_off = (uint32_t)(j16 >> 1) * (uint32_t)a.HP * 16u + (uint32_t)(j16 & 1) * 8u;
+      const float* tabc = a.tab3 + t_kb * a.KB + j16 * 4;
+      const int* ri = rowinfo + (t_par * a.J + t_j) * a.HP;
       // (mean, rstd*G, S) of this thread's 4 channels for the image of the current row: a slab touches one or two
-      // images on the large maps, so the three L1 loads are paid once per K-block, not once per row
+      // images on the large maps, so the three L1 loads are paid once per job, not once per row
       float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), tg = tm, ts = tm;
       int tb_img = -1;
+      if (!(a.dbgf & 1)) {
 #pragma unroll 4
-      for (int h = hrow; h < hhi && !(a.dbgf & 1); h += RPP) {
-        if (h < hlo) continue;
-        const int2 info = rowinfo[par * a.HP + h];
-        float4 x;
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                     : "r"(rst + (uint32_t)((h << pj_shift) + j) * 16u));
-        uint32_t h0 = 0u, h1 = 0u, l0 = 0u, l1 = 0u;
-        if (info.x >= 0) {
-          float v[4] = {x.x, x.y, x.z, x.w};
-          if (norm) {
-            if (info.y != tb_img) {
-              const float* tb = tabc + (long long)info.y * 3 * Cin;
-              tm = __ldg(reinterpret_cast<const float4*>(tb));
-              tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
-              ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
-              tb_img = info.y;
+        for (int h = hrow; h < hhi; h += RPP) {
+          if (h < hlo) continue;
+          const int pix = ri[h];
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(rst + (uint32_t)((h << pj_shift) + j16) * 16u));
+          uint32_t h0 = 0u, h1 = 0u, l0 = 0u, l1 = 0u;
+          if (pix >= 0) {
+            float v[4] = {x.x, x.y, x.z, x.w};
+            if (norm) {
+              const int img = pix / a.HW;
+              if (img != tb_img) {
+                const float* tb = tabc + (long long)img * 3 * Cin;
+                tm = __ldg(reinterpret_cast<const float4*>(tb));
+                tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
+                ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
+                tb_img = img;
+              }
+              v[0] = fmaf(v[0] - tm.x, tg.x, ts.x); v[1] = fmaf(v[1] - tm.y, tg.y, ts.y);
+              v[2] = fmaf(v[2] - tm.z, tg.z, ts.z); v[3] = fmaf(v[3] - tm.w, tg.w, ts.w);
+              if (a.act_in) silu_fast4(v);
             }
-            v[0] = fmaf(v[0] - tm.x, tg.x, ts.x); v[1] = fmaf(v[1] - tm.y, tg.y, ts.y);
-            v[2] = fmaf(v[2] - tm.z, tg.z, ts.z); v[3] = fmaf(v[3] - tm.w, tg.w, ts.w);
-            if (a.act_in) silu_fast4(v);
+            split2_sat(v[0], v[1], h0, l0);
+            split2_sat(v[2], v[3], h1, l1);
           }
-          split2_sat(v[0], v[1], h0, l0);
-          split2_sat(v[2], v[3], h1, l1);
+          const uint32_t off = img_off + (uint32_t)h * 16u;
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_base + off), "r"(h0), "r"(h1) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_base + off), "r"(l0), "r"(l1) : "memory");
         }
-        const uint32_t off = img_off + (uint32_t)h * 16u;
-        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_base + off), "r"(h0), "r"(h1) : "memory");
-        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_base + off), "r"(l0), "r"(l1) : "memory");
       }
       DBG_ADD(3, tp, tid == 0);
       fence_proxy_async();                // generic-proxy smem stores -> visible to the tensor-core (async) proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(A_FULL(st));          // one arrival per producer warp
+      if (lane == 0) {                    // one arrival per producer warp, on the LEADER's barrier
+        if (rank == 0) mbar_arrive(A_FULL(st)); else mbar_arrive_remote(a_full_leader + 8u * st);
+      }
       DBG_ADD(4, tp, tid == 0);
-      if (++t_kb == a.nKB) { t_kb = 0; ++t_unit; }
+      if (++t_j == t_cnt) {
+        t_j = 0;
+        if (++t_kb == a.nKB) { t_kb = 0; ut.next(t_nt, t_pt0, t_cnt); t_par ^= 1; }
+      }
     }
   } else if (warp == W_LOAD) {
-    // =============================== weight loader ===============================
+    // =============================== weight loader (both CTAs) ===============================
     if (elect_one()) {
       const uint32_t b0 = sbase + a.off_b;
-      int st = 0, ph = 1;
-      for (int iu = 0; iu < ((a.dbgf & 32) ? 0 : my_units); ++iu) {
-        const int u = cid + iu * ncl;
-        const uint8_t* wsrc = a.wpk + ((size_t)(u % a.tiles_n) * per_unit * 2 + rank) * a.b_stage;
+      const uint32_t b_full_leader = mapa_u32(B_FULL(0), 0);
+      const int per_unit = a.nKB0 * taps + (a.nKB - a.nKB0);       // weight stages per unit
+      Units un(a, cid, ncl);
+      int nt, pt0, cnt, st = 0, ph = 1;
+      while (un.next(nt, pt0, cnt)) {
+        const int row0 = (nt * per_unit * 2 + (int)rank) * (int)a.b_rows;
         for (int i = 0; i < per_unit; ++i) {
-          mbar_wait(B_EMPTY(st), ph);
-          if (a.dbgf & 4) { mbar_arrive(B_FULL(st)); if (++st == NB) { st = 0; ph ^= 1; } continue; }
-          mbar_arrive_expect_tx(B_FULL(st), a.b_stage);
-          bulk_g2s(b0 + (uint32_t)st * a.b_stage, wsrc + (size_t)i * 2 * a.b_stage, a.b_stage, B_FULL(st));
+          if (a.dbgf & 8) mbar_wait(B_EMPTY(st), ph); else mbar_wait_parked(B_EMPTY(st), ph);
+          if (rank == 0) mbar_arrive_expect_tx(B_FULL(st), 2u * a.b_stage);     // both halves report here
+          if (a.dbgf & 4) {
+            // timing switch: no reload; complete the transaction count by hand
+            asm volatile("mbarrier.complete_tx.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(b_full_leader + 8u * st),
+                         "r"(a.b_stage) : "memory");
+          } else {
+            tma_load_stage(b0 + (uint32_t)st * a.b_stage, &wmap, row0 + i * 2 * (int)a.b_rows, b_full_leader + 8u * st);
+          }
           if (++st == NB) { st = 0; ph ^= 1; }
         }
       }
@@ -299,182 +353,209 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
   } else if (warp == W_MMA) {
     if (rank == 0) {
       // =============================== MMA issuer (leader CTA) ===============================
-      if (elect_one()) {
-        const uint32_t idesc = make_idesc_f16(2 * MT, a.NT);
-        const uint32_t a_lbo16 = (uint32_t)a.HP, b_lbo16 = (uint32_t)(a.NT >> 1);
-        const uint64_t a_proto = make_desc(0, a_lbo16 * 16, 128), b_proto = make_desc(0, b_lbo16 * 16, 128);
-        const int ksteps = a.KB / 16;
-        const uint32_t a_plane16 = a.a_plane >> 4, b_step16 = (32u * a.NT) >> 4, b_lo16 = (16u * a.NT) >> 4;
-        const uint32_t a0_16 = (sbase + a.off_img) >> 4, b0_16 = (sbase + a.off_b) >> 4;
-        const uint32_t a_stage16 = 2 * a_plane16, b_stage16 = a.b_stage >> 4;
-        const bool w_lo = (a.split & 2) != 0, a_lo = (a.split & 1) != 0;
-        int bst = 0, bph = 0, g = 0;
-        for (int iu = 0; iu < my_units; ++iu) {
-          const int set = iu & 1;
-          DBG_T(tm);
-          mbar_wait_cluster(ACC_EMPTY(set), ((iu >> 1) & 1) ^ 1);    // both epilogues drained this set
-          DBG_ADD(5, tm, true);
-          tc_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(set * a.NT);
-          uint32_t accum = 0;
-          for (int kb = 0; kb < a.nKB; ++kb, ++g) {
-            const int st = g % SA;
-            const uint32_t aph = (uint32_t)((g / SA) & 1);
-            DBG_ADD(8, tm, true);
-            if (!(a.dbgf & 16)) {
-              mbar_wait(A_FULL(st), aph);
-              if (!(a.dbgf & 8)) mbar_wait_cluster(PA_FULL(st), aph);
-            }
-            DBG_ADD(6, tm, true);
-            // no tcgen05.fence here: the slab was written through the generic proxy and published with
-            // fence.proxy.async + mbarrier release/acquire; a tcgen05.fence::after_thread_sync per stage drained
-            // the MMA pipeline (~500 cycles per weight stage in round 1 and in the first version of this kernel)
-            const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
-            const bool main = kb < a.nKB0;
-            const int ntap = main ? taps : 1;
-            for (int tap = 0; tap < ntap; ++tap) {
-              DBG_ADD(8, tm, true);
-              if (!(a.dbgf & 32)) {
-                mbar_wait(B_FULL(bst), bph);
-                if (!(a.dbgf & 8)) mbar_wait_cluster(PB_FULL(bst), bph);
+      // The WHOLE warp walks the loops (warp-uniform control flow and address arithmetic, which the compiler keeps
+      // on the uniform datapath); only the tcgen05.mma / tcgen05.commit instructions sit under elect.sync.  A
+      // single-thread loop with per-MMA descriptor arithmetic was issue-bound at ~150-290 cycles per MMA, 3-6x the
+      // tensor time (profiles/r2_conv2_isolation.txt).  Descriptors differ only in their low word (start address
+      // field, < 2^14 16-byte units, never carries into the LBO field).  The waits are plain (CTA-scope acquire)
+      // try_waits: an .acquire.cluster wait compiles to TRYWAIT + CCTL.IVALL (an L1 invalidation per weight stage),
+      // and nothing this thread reads afterwards needs it -- the operands are read by each SM's tensor core from
+      // its own shared memory, published by fence.proxy.async (slabs) or written by TMA (weights).
+      const uint32_t idesc = make_idesc_f16(2 * MT, a.NT);
+      const uint64_t a_proto = make_desc(0, (uint32_t)a.HP * 16, 128), b_proto = make_desc(0, (uint32_t)(a.NT >> 1) * 16, 128);
+      const uint32_t a_hiw = (uint32_t)(a_proto >> 32), b_hiw = (uint32_t)(b_proto >> 32);
+      const uint32_t a_low = (uint32_t)a_proto, b_low = (uint32_t)b_proto;
+      const uint32_t a_plane16 = a.a_plane >> 4, b_step16 = (32u * a.NT) >> 4, b_lo16 = (16u * a.NT) >> 4;
+      const uint32_t a_kstep16 = 2u * (uint32_t)a.HP;
+      const uint32_t a_stage16 = 2 * a_plane16, b_stage16 = a.b_stage >> 4;
+      const uint32_t a_org = a_low + ((sbase + a.off_img) >> 4) + (uint32_t)a.halo0;      // low word of stage 0, centre tap
+      const uint32_t b_org = b_low + ((sbase + a.off_b) >> 4);
+      const bool w_lo = (a.split & 2) != 0, a_lo = (a.split & 1) != 0;
+      auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+      Units un(a, cid, ncl);
+      int nt, pt0, cnt, bst = 0, ast = 0, iu = 0;
+      uint32_t bph = 0, aph = 0;
+      uint32_t b_cur = b_org;                               // low descriptor word of weight stage bst
+      while (un.next(nt, pt0, cnt)) {
+        const int set = iu % a.nsets;
+        const uint32_t acc_ph = (uint32_t)((iu / a.nsets) & 1);
+        DBG_T(tm);
+        for (int j = 0; j < cnt; ++j) mbar_wait_parked(ACC_EMPTY(set * JMAX + j), acc_ph ^ 1);   // epilogues drained them
+        DBG_ADD(5, tm, lane == 0);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + (uint32_t)(set * a.J * a.NT);
+        for (int kb = 0; kb < a.nKB; ++kb) {
+          DBG_ADD(8, tm, lane == 0);
+          // the cnt slabs of this K-block: stages ast .. ast+cnt-1 (mod SA); low descriptor words per tile
+          uint32_t a_j[JMAX];
+          {
+            int st = ast;
+            uint32_t ph = aph;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+              if (j < cnt) {
+                if (a.dbgf & 8) mbar_wait(A_FULL(st), ph); else mbar_wait_parked(A_FULL(st), ph);
+                a_j[j] = a_org + (uint32_t)st * a_stage16;
+                if (++st == SA) { st = 0; ph ^= 1; }
               }
-              DBG_ADD(7, tm, true);
-              const int shift = (a.ks == 3 && main) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
-              const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
-              const uint32_t b_tap16 = b0_16 + (uint32_t)bst * b_stage16;
-              for (int s = 0; s < ksteps; ++s) {
-                const uint64_t dbh = desc_add(b_proto, b_tap16 + (uint32_t)s * b_step16);
-                const uint64_t dbl = desc_add(dbh, b_lo16);
-                const uint64_t dah = desc_add(a_proto, a_tap16 + (uint32_t)(2 * s) * a_lbo16);
-                const uint64_t dal = desc_add(dah, a_plane16);
-                umma2_f16(d, dah, dbh, idesc, accum);
-                if (a_lo) umma2_f16(d, dal, dbh, idesc, 1u);
-                if (w_lo) umma2_f16(d, dah, dbl, idesc, 1u);
-                accum = 1u;
-              }
-              umma2_commit_mc(B_EMPTY(bst));       // weight stage consumed (both CTAs)
-              if (++bst == NB) { bst = 0; bph ^= 1; }
-            }
-            umma2_commit_mc(A_EMPTY(st));          // slab stage consumed (both CTAs)
-          }
-          umma2_commit_mc(ACC_FULL(set));
-          DBG_ADD(8, tm, true);
-        }
-      }
-    } else {
-      // ===================== peer CTA: forward "stage filled" to the leader's barriers =====================
-      if (elect_one()) {
-        int bst = 0, bph = 0, g = 0;
-        for (int iu = 0; iu < my_units; ++iu) {
-          for (int kb = 0; kb < a.nKB; ++kb, ++g) {
-            const int st = g % SA;
-            if (!(a.dbgf & 16)) {
-              mbar_wait(A_FULL(st), (uint32_t)((g / SA) & 1));
-              mbar_arrive_remote(mapa_u32(PA_FULL(st), 0));
-            }
-            const int ntap = (kb < a.nKB0) ? taps : 1;
-            for (int tap = 0; tap < ntap; ++tap) {
-              if (!(a.dbgf & 32)) {
-                mbar_wait(B_FULL(bst), bph);
-                mbar_arrive_remote(mapa_u32(PB_FULL(bst), 0));
-              }
-              if (++bst == NB) { bst = 0; bph ^= 1; }
             }
           }
+          DBG_ADD(6, tm, lane == 0);
+          const bool main = kb < a.nKB0;
+          const int ntap = main ? taps : 1;
+          int dy = -1, dx = -1;                              // tap offsets (3x3 main segment), (0, 0) otherwise
+          if (ntap == 1) { dy = 0; dx = 0; }
+          for (int tap = 0; tap < ntap; ++tap) {
+            DBG_ADD(8, tm, lane == 0);
+            if (a.dbgf & 8) mbar_wait(B_FULL(bst), bph); else mbar_wait_parked(B_FULL(bst), bph);
+            DBG_ADD(7, tm, lane == 0);
+            const uint32_t shift = (uint32_t)(dy * a.Wp + dx);
+            const uint32_t first = (kb > 0 || tap > 0) ? 1u : 0u;      // 0 only for the first MMA of an accumulator
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < JMAX; ++j) {
+                if (j < cnt) {
+                  const uint32_t d = d0 + (uint32_t)(j * a.NT);
+                  uint32_t al = a_j[j] + shift, bl = b_cur;
+#pragma unroll
+                  for (int s = 0; s < KSTEPS; ++s) {
+                    const uint64_t dah = desc(al, a_hiw), dal = desc(al + a_plane16, a_hiw);
+                    const uint64_t dbh = desc(bl, b_hiw), dbl = desc(bl + b_lo16, b_hiw);
+                    umma2_f16(d, dah, dbh, idesc, (s > 0) ? 1u : first);
+                    if (a_lo) umma2_f16(d, dal, dbh, idesc, 1u);
+                    if (w_lo) umma2_f16(d, dah, dbl, idesc, 1u);
+                    al += a_kstep16; bl += b_step16;
+                  }
+                }
+              }
+              umma2_commit_mc(B_EMPTY(bst));           // weight stage consumed (both CTAs)
+            }
+            __syncwarp();
+            b_cur += b_stage16;
+            if (++bst == NB) { bst = 0; bph ^= 1; b_cur = b_org; }
+            if (++dx == 2) { dx = -1; ++dy; }
+          }
+          if (elect_one()) {
+            int st = ast;
+#pragma unroll
+            for (int j = 0; j < JMAX; ++j) {
+              if (j < cnt) {
+                umma2_commit_mc(A_EMPTY(st));          // slab stages consumed (both CTAs)
+                if (++st == SA) st = 0;
+              }
+            }
+          }
+          __syncwarp();
+          ast += cnt;
+          if (ast >= SA) { ast -= SA; aph ^= 1; }
         }
+        if (elect_one())
+          for (int j = 0; j < cnt; ++j) umma2_commit_mc(ACC_FULL(set * JMAX + j));
+        __syncwarp();
+        DBG_ADD(8, tm, lane == 0);
+        ++iu;
       }
     }
     __syncwarp();
   } else {
     // =============================== epilogue ===============================
-    // Each of the 4 warps drains its 32 TMEM lanes (rows) in column blocks of 32 (or a 16-wide tail) through an
-    // XOR-swizzled 4 KB transpose pad, so global loads / stores cover whole 128-byte lines of dst / res.
-    const int lq = warp & 3;
-    const int et = tid - W_EPI * 32;
-    float4* pad = reinterpret_cast<float4*>(smem + a.off_pad) + (size_t)(warp - W_EPI) * 256;
-    float* bias_s = reinterpret_cast<float*>(smem + a.off_bias);
-    unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(smem + a.off_stat);
+    // Two groups of four warps (TMEM lane quadrants); group e owns position tiles j = e, e+2 of every unit.  A warp
+    // drains its 32 TMEM lanes (rows) in column blocks of 32 (or a 16-wide tail) through an XOR-swizzled 4 KB
+    // transpose pad, so global loads / stores cover whole 128-byte lines of dst / res.
+    const int ew = warp - W_EPI, grp = ew >> 2, lq = warp & 3;
+    const int et = tid - (W_EPI + 4 * grp) * 32;                                // 0..127 inside the group
+    float4* pad = reinterpret_cast<float4*>(smem + a.off_pad) + (size_t)ew * 256;
+    float* bias_s = reinterpret_cast<float*>(smem + a.off_bias) + grp * 256;
+    unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(smem + a.off_stat) + (size_t)grp * a.NJ * 2 * a.NT;
     const int nblk = (a.NT + 31) / 32;
     const float* __restrict__ resp = a.res;
     float* __restrict__ dstp = a.dst;
     const uint32_t acc_empty_leader = mapa_u32(ACC_EMPTY(0), 0);
-    for (int iu = 0; iu < my_units; ++iu) {
-      const int u = cid + iu * ncl;
-      const int set = iu & 1;
-      const int mtile = (u / a.tiles_n) * 2 + (int)rank;               // 128-row tile index
-      const long long p0 = (long long)mtile * MT;
-      const int n0 = (u % a.tiles_n) * a.NT;
-      named_bar_sync(2, 128);                                         // previous unit's readers are done
-      for (int i = et; i < a.NT; i += 128) bias_s[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
-      named_bar_sync(2, 128);
-      int myb;
-      const int mypix = decode_pos(a, p0 + lq * 32 + lane, myb);
-      const int tile_b0 = (int)min((long long)(a.B - 1), p0 / a.Pimg);
-      const int myj = mypix >= 0 ? myb - tile_b0 : -1;                 // image slot of this row (stats)
-      int px8[8];
+    const int bar_id = 2 + grp;
+    Units un(a, cid, ncl);
+    int nt, pt0, cnt, iu = 0;
+    while (un.next(nt, pt0, cnt)) {
+      const int set = iu % a.nsets;
+      const uint32_t acc_ph = (uint32_t)((iu / a.nsets) & 1);
+      ++iu;
+      const int n0 = nt * a.NT;
+      for (int j = grp; j < cnt; j += 2) {
+        const int mtile = (pt0 + j) * 2 + (int)rank;                          // 128-row tile index
+        const long long p0 = (long long)mtile * MT;
+        named_bar_sync(bar_id, 128);                                         // previous tile's readers are done
+        for (int i = et; i < a.NT; i += 128) bias_s[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
+        named_bar_sync(bar_id, 128);
+        const int mypix = decode_pos(a, p0 + lq * 32 + lane);
+        const int tile_b0 = (int)min((long long)(a.B - 1), p0 / a.Pimg);
+        const int myj = mypix >= 0 ? mypix / a.HW - tile_b0 : -1;              // image slot of this row (stats)
+        int px8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) px8[k] = __shfl_sync(0xffffffffu, mypix, k * 4 + (lane >> 3));
-      const int q8 = lane & 7;
-      unsigned jmask = 0;                                             // image slots present in this warp's rows
-      if (a.stats) {
+        for (int k = 0; k < 8; ++k) px8[k] = __shfl_sync(0xffffffffu, mypix, k * 4 + (lane >> 3));
+        unsigned jmask = 0;                                                   // image slots present in this warp's rows
+        if (a.stats) {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          if (__ballot_sync(0xffffffffu, myj == jj)) jmask |= 1u << jj;
-      }
-      float4 rnext[8];
-      auto res_fetch = [&](int blk) {
-        if (!resp) return;
-        const int cb = blk * 32;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (px8[k] >= 0) rnext[k] = ld_nc_na(resp + (long long)px8[k] * a.Cout + n0 + cb + q8 * 4);
-      };
-      if (a.NT >= 32) res_fetch(0);
-      DBG_T(te);
-      if (lane == 0) mbar_wait(ACC_FULL(set), (uint32_t)((iu >> 1) & 1));
-      __syncwarp();
-      DBG_ADD(9, te, tid == W_EPI * 32);
-      tc_fence_after();
-      const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(set * a.NT);
-      if (a.dbgf & 2) {
-        tc_fence_before();
-        if (rank == 0) mbar_arrive(ACC_EMPTY(set)); else mbar_arrive_remote(acc_empty_leader + 8u * set);
-        continue;
-      }
-      for (int blk = 0; blk < nblk; ++blk) {
-        const int cb = blk * 32;
-        const int w = min(32, a.NT - cb);
-        uint32_t r[32];
-        tmem_ld16(trow0 + (uint32_t)cb, r);
-        if (w == 32) tmem_ld16(trow0 + (uint32_t)(cb + 16), r + 16);
-        tmem_ld_wait();
-        if (blk == nblk - 1) {                       // accumulator fully read: hand the TMEM set back
-          tc_fence_before();
-          if (rank == 0) mbar_arrive(ACC_EMPTY(set)); else mbar_arrive_remote(acc_empty_leader + 8u * set);
+          for (int jj = 0; jj < 4; ++jj)
+            if (__ballot_sync(0xffffffffu, myj == jj)) jmask |= 1u << jj;
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q * 4 < w)
-            pad[lane * 8 + (q ^ (lane & 7))] =
-                make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
-                            __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
+        DBG_T(te);
+        if (lane == 0) { if (a.dbgf & 8) mbar_wait(ACC_FULL(set * JMAX + j), acc_ph); else mbar_wait_parked(ACC_FULL(set * JMAX + j), acc_ph); }
         __syncwarp();
-        if (w == 32) {
-          float4 rcur[8];
+        DBG_ADD(9, te, et == 0);
+        tc_fence_after();
+        const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((set * a.J + j) * a.NT);
+        for (int blk = 0; blk < nblk; ++blk) {
+          const int cb = blk * 32;
+          const int w = min(32, a.NT - cb);
+          const bool wide = (w == 32);
+          float4 rres[8];
+          if (resp && wide && !(a.dbgf & 2)) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) rcur[k] = rnext[k];
-          if ((blk + 1) * 32 + 32 <= a.NT) res_fetch(blk + 1);
-          const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q8 * 4);
+            for (int k = 0; k < 8; ++k)
+              if (px8[k] >= 0) rres[k] = ld_nc_na(resp + (long long)px8[k] * a.Cout + n0 + cb + (lane & 7) * 4);
+          }
+          uint32_t r[32];
+          tmem_ld16(trow0 + (uint32_t)cb, r);
+          if (wide) tmem_ld16(trow0 + (uint32_t)(cb + 16), r + 16);
+          tmem_ld_wait();
+          if (blk == nblk - 1) {                       // accumulator fully read: hand it back (one arrive per warp)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (rank == 0) mbar_arrive(ACC_EMPTY(set * JMAX + j));
+              else mbar_arrive_remote(acc_empty_leader + 8u * (set * JMAX + j));
+            }
+          }
+          if (a.dbgf & 2) continue;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q * 4 < w)
+              pad[lane * 8 + (q ^ (lane & 7))] =
+                  make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
+                              __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
+          __syncwarp();
+          // transposed phase: 8 lanes per row (32-wide block) or 4 lanes per row (16-wide tail)
+          const int lpr = wide ? 8 : 4;
+          const int qc = lane & (lpr - 1), rsub = wide ? (lane >> 3) : (lane >> 2);
+          const int rpi = wide ? 4 : 8;                       // rows per instruction
+          const int nk = wide ? 8 : 4;
+          const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + qc * 4);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const int row = k * 4 + (lane >> 3);
-            float4 v = pad[row * 8 + (q8 ^ (row & 7))];
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            if (resp && px8[k] >= 0) { v.x += rcur[k].x; v.y += rcur[k].y; v.z += rcur[k].z; v.w += rcur[k].w; }
-            v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
-            if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-            if (px8[k] >= 0) *reinterpret_cast<float4*>(dstp + (long long)px8[k] * a.Cout + n0 + cb + q8 * 4) = v;
-            if (a.stats) pad[row * 8 + (q8 ^ (row & 7))] = v;      // same thread re-reads it below
+            if (k < nk) {
+              const int row = k * rpi + rsub;
+              const int px = wide ? px8[k] : __shfl_sync(0xffffffffu, mypix, row);
+              float4 v = pad[row * 8 + (qc ^ (row & 7))];
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              const long long off = (long long)px * a.Cout + n0 + cb + qc * 4;
+              if (resp && px >= 0) {
+                const float4 rv = wide ? rres[k] : ld_nc_na(resp + off);
+                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+              }
+              v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
+              if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+              if (px >= 0) *reinterpret_cast<float4*>(dstp + off) = v;
+              if (a.stats) pad[row * 8 + (qc ^ (row & 7))] = v;      // same thread re-reads it below
+            }
           }
           if (a.stats) {
 #pragma unroll 1
@@ -484,86 +565,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
               unsigned long long s2[4] = {0, 0, 0, 0};
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const int row = k * 4 + (lane >> 3);
-                if (__shfl_sync(0xffffffffu, myj, row) == jj) {
-                  const float4 v = pad[row * 8 + (q8 ^ (row & 7))];
-                  const float f[4] = {v.x, v.y, v.z, v.w};
+                if (k < nk) {
+                  const int row = k * rpi + rsub;
+                  if (__shfl_sync(0xffffffffu, myj, row) == jj) {
+                    const float4 v = pad[row * 8 + (qc ^ (row & 7))];
+                    const float f[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    int xi = __float2int_rn(f[e] * STAT_SCALE);
-                    xi = max(-STAT_CLAMP, min(STAT_CLAMP, xi));
-                    s1[e] += xi;
-                    s2[e] += (unsigned long long)((long long)xi * (long long)xi);
+                    for (int e = 0; e < 4; ++e) {
+                      const int xi = __float2int_rn(f[e] * STAT_SCALE);       // saturates at +-2^31
+                      s1[e] += xi;
+                      s2[e] += (unsigned long long)((long long)xi * (long long)xi);
+                    }
                   }
                 }
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 8);
-                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], 16);
-                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 8);
-                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], 16);
-              }
-              if (lane < 8) {
-                unsigned long long* sp = stat_s + (size_t)jj * 2 * a.NT + cb + q8 * 4;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  atomicAdd(sp + e, (unsigned long long)s1[e]);
-                  atomicAdd(sp + a.NT + e, s2[e]);
-                }
-              }
-            }
-          }
-        } else {                                          // 16-wide tail: 4 lanes per row, 8 rows per instruction
-          const int q = lane & 3, rsub = lane >> 2;
-          const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int row = k * 8 + rsub;
-            const int px = __shfl_sync(0xffffffffu, mypix, row);
-            float4 v = pad[row * 8 + (q ^ (row & 7))];
-            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-            const long long off = (long long)px * a.Cout + n0 + cb + q * 4;
-            if (resp && px >= 0) {
-              const float4 rv = ld_nc_na(resp + off);
-              v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-            }
-            v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
-            if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-            if (px >= 0) *reinterpret_cast<float4*>(dstp + off) = v;
-            if (a.stats) pad[row * 8 + (q ^ (row & 7))] = v;
-          }
-          if (a.stats) {
-#pragma unroll 1
-            for (int jj = 0; jj < 4; ++jj) {
-              if (!(jmask & (1u << jj))) continue;
-              long long s1[4] = {0, 0, 0, 0};
-              unsigned long long s2[4] = {0, 0, 0, 0};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int row = k * 8 + rsub;
-                if (__shfl_sync(0xffffffffu, myj, row) == jj) {
-                  const float4 v = pad[row * 8 + (q ^ (row & 7))];
-                  const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    int xi = __float2int_rn(f[e] * STAT_SCALE);
-                    xi = max(-STAT_CLAMP, min(STAT_CLAMP, xi));
-                    s1[e] += xi;
-                    s2[e] += (unsigned long long)((long long)xi * (long long)xi);
-                  }
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-#pragma unroll
-                for (int o = 4; o <= 16; o <<= 1) {
+                for (int o = lpr; o <= 16; o <<= 1) {
                   s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
                   s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
                 }
               }
-              if (lane < 4) {
-                unsigned long long* sp = stat_s + (size_t)jj * 2 * a.NT + cb + q * 4;
+              if (lane < lpr) {
+                unsigned long long* sp = stat_s + (size_t)jj * 2 * a.NT + cb + qc * 4;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   atomicAdd(sp + e, (unsigned long long)s1[e]);
@@ -572,20 +596,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_conv_
               }
             }
           }
+          __syncwarp();
         }
-        __syncwarp();
-      }
-      if (a.stats) {
-        // the four warps' contributions to this 128-row tile -> global [tile][NJ][2][Cout], then re-zero
-        named_bar_sync(2, 128);
-        unsigned long long* gp = a.stats + (size_t)mtile * a.NJ * 2 * a.Cout;
-        for (int i = et; i < a.NJ * 2 * a.NT; i += 128) {
-          const int jp = i / a.NT, n = i - jp * a.NT;
-          gp[(size_t)jp * a.Cout + n0 + n] = stat_s[i];
-          stat_s[i] = 0ull;
+        if (a.stats && !(a.dbgf & 2)) {
+          // the four warps' contributions to this 128-row tile -> global [tile][NJ][2][Cout], then re-zero
+          named_bar_sync(bar_id, 128);
+          unsigned long long* gp = a.stats + (size_t)mtile * a.NJ * 2 * a.Cout;
+          for (int i = et; i < a.NJ * 2 * a.NT; i += 128) {
+            const int jp = i / a.NT, n = i - jp * a.NT;
+            gp[(size_t)jp * a.Cout + n0 + n] = stat_s[i];
+            stat_s[i] = 0ull;
+          }
         }
+        DBG_ADD(10, te, et == 0);
       }
-      DBG_ADD(10, te, tid == W_EPI * 32);
     }
   }
 
@@ -633,19 +657,19 @@ __global__ void k_pack_weights2(const float* __restrict__ w, __half* __restrict_
 }
 
 struct Plan {
-  int KB, NT, HP, halo0, SA, R, NB, NJ, Wp, Pimg, tmem_cols;
+  int KB, NT, HP, halo0, SA, R, NB, NJ, J, nsets, Wp, Pimg, tmem_cols;
   uint32_t off_img, off_raw, off_b, off_pad, off_row, off_stat, off_bias, off_bar, a_plane, raw_stage, b_stage;
   size_t smem;
 };
 
-int kb_of(int C0, int C1, int C2, int C3) {
+int kb_max(int C0, int C1, int C2, int C3) {
   auto ok = [](int c, int m) { return c % m == 0; };
   if (ok(C0, 32) && ok(C1, 32) && ok(C2, 32) && ok(C3, 32)) return 32;
   if (ok(C0, 16) && ok(C1, 16) && ok(C2, 16) && ok(C3, 16)) return 16;
   return 0;
 }
 
-// shared-memory plan for one conv; returns false when nothing fits
+// shared-memory plan for one conv; returns false when it does not fit
 bool make_plan(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, int KB, bool stats, Plan& p) {
   p.KB = KB; p.NT = NT;
   if (ks == 3) { p.Wp = W + 1; p.Pimg = (H + 1) * (W + 1); p.halo0 = p.Wp + 1; }
@@ -658,32 +682,31 @@ bool make_plan(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, int
   p.a_plane = (uint32_t)(KB / 8) * hp * 16;
   p.raw_stage = (uint32_t)hp * KB * 4;
   p.b_stage = (uint32_t)(KB / 16) * 32 * NT;
+  // tiles per unit: as many accumulators as fit twice into TMEM (double-buffered sets), at most JMAX
+  int J = 256 / NT;
+  if (J > JMAX) J = JMAX;
+  if (J < 1) J = 1;
+  p.J = J;
+  p.nsets = (2 * J * NT <= 512) ? 2 : 1;
   const int nKB0 = (C0 + C1) / KB, nKB = nKB0 + (C2 + C3) / KB;
-  const size_t stat_bytes = stats ? (size_t)p.NJ * 2 * NT * 8 : 0;
-  const size_t fixed = 4 * 4096 + (size_t)2 * hp * 8 + stat_bytes + 1024 + 1024;
+  const size_t stat_bytes = stats ? (size_t)2 * p.NJ * 2 * NT * 8 : 0;
+  const size_t row_bytes = (size_t)2 * J * hp * 4;
+  const size_t fixed = (size_t)NEPI_W * 4096 + row_bytes + stat_bytes + 2 * 1024 + 1024;
   const size_t limit = 227 * 1024;
   const size_t a_stage = 2 * (size_t)p.a_plane;
-  int SA = 2, R = 2, NB = 3;
-  if (fixed + SA * a_stage + R * (size_t)p.raw_stage + NB * (size_t)p.b_stage > limit) return false;
-  // grow: weights ring first (to 4), then the raw ring / image stages of short K-blocks (1x1), then weights again
+  // minimum: the J slabs of a K-block resident + one being filled, 2 raw stages, 4 weight stages
+  int SA = J + 1, R = 2, NB = 4;
   auto fits = [&](int sa, int r, int nb) {
     return fixed + sa * a_stage + r * (size_t)p.raw_stage + nb * (size_t)p.b_stage <= limit;
   };
-  while (NB < 4 && fits(SA, R, NB + 1)) ++NB;
-  const int r_max = (nKB + 1 < 4) ? nKB + 1 : 4;         // prefetch distance R-1 <= K-blocks per unit
-  if (ks == 1) {
-    while ((R < r_max || SA < 4) ) {
-      bool grew = false;
-      if (R < r_max && fits(SA, R + 1, NB)) { ++R; grew = true; }
-      if (SA < 4 && fits(SA + 1, R, NB)) { ++SA; grew = true; }
-      if (!grew) break;
-    }
-  }
+  if (!fits(SA, R, NB)) return false;
+  const int r_max = (nKB + 1 < 4) ? nKB + 1 : 4;         // prefetch distance R-1 <= K-blocks (>= jobs) per unit
+  // grow in the order that matters: weight ring to 8, slabs to 2J (next K-block fully buffered), raw ring, weights
   while (NB < 8 && fits(SA, R, NB + 1)) ++NB;
-  if (ks == 3) {
-    if (R < r_max && R < 3 && fits(SA, R + 1, NB)) ++R;
-    if (SA < 3 && fits(SA + 1, R, NB)) ++SA;
-  }
+  while (SA < 2 * J && fits(SA + 1, R, NB)) ++SA;
+  while (R < r_max && R < 3 && fits(SA, R + 1, NB)) ++R;
+  while (NB < 16 && fits(SA, R, NB + 1)) ++NB;
+  while (R < r_max && fits(SA, R + 1, NB)) ++R;
   if (R > r_max) R = r_max;
   if (R < 2) R = 2;
   p.SA = SA; p.R = R; p.NB = NB;
@@ -693,22 +716,24 @@ bool make_plan(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, int
   off = (off + 127) & ~(size_t)127;
   p.off_b = (uint32_t)off; off += NB * (size_t)p.b_stage;
   off = (off + 127) & ~(size_t)127;
-  p.off_pad = (uint32_t)off; off += 4 * 4096;
-  p.off_row = (uint32_t)off; off += (size_t)2 * hp * 8;
+  p.off_pad = (uint32_t)off; off += (size_t)NEPI_W * 4096;
+  p.off_row = (uint32_t)off; off += row_bytes;
   off = (off + 15) & ~(size_t)15;
   p.off_stat = (uint32_t)off; off += stat_bytes;
-  p.off_bias = (uint32_t)off; off += 1024;
-  p.off_bar = (uint32_t)off; off += 8 * (3 * SA + 3 * NB + 4) + 16;
+  p.off_bias = (uint32_t)off; off += 2 * 1024;
+  p.off_bar = (uint32_t)off; off += 8 * (2 * SA + 2 * NB + 4 * JMAX) + 16;
   p.smem = off;
-  int cols = 2 * NT, p2 = 32;
+  int cols = p.nsets * J * NT, p2 = 32;
   while (p2 < cols) p2 <<= 1;
   p.tmem_cols = p2;
   return off <= limit && p2 <= 512;
 }
 
-// K-block size: 32 channels when every source allows it and the slab fits, else 16
+// K-block size: 3x3 convs use 16 channels (the J slabs of a K-block and their successors must be co-resident),
+// 1x1 convs 32 when every source allows it
 int plan_kb(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, bool stats) {
-  int kb = kb_of(C0, C1, C2, C3);
+  int kb = kb_max(C0, C1, C2, C3);
+  if (ks == 3 && kb > 16) kb = 16;
   Plan p;
   while (kb >= 16) {
     if (make_plan(H, W, ks, C0, C1, C2, C3, NT, kb, stats, p)) return kb;
@@ -717,39 +742,57 @@ int plan_kb(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, bool s
   return 0;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 }  // namespace
 
 int launch_conv_umma2(const McvdOp& op, cudaStream_t s) {
-  MCVD_CHECK(op.src0 && op.w && op.dst && (op.C1 == 0 || op.src1), "CONV_UMMA: null pointer");
-  MCVD_CHECK(op.i0 == 1 || op.i0 == 3, "CONV_UMMA: kernel size %d unsupported", op.i0);
+  MCVD_CHECK(op.src0 && op.w && op.dst && (op.C1 == 0 || op.src1), "CONV_UMMA2: null pointer");
+  MCVD_CHECK(op.i0 == 1 || op.i0 == 3, "CONV_UMMA2: kernel size %d unsupported", op.i0);
   C2Args a;
   memset(&a, 0, sizeof(a));
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1;
   a.s2 = (const float*)op.src2; a.s3 = (const float*)op.src3;
   a.C0 = op.C0; a.C1 = op.C1; a.C2 = op.src2 ? op.C2 : 0; a.C3 = op.src3 ? op.C3 : 0;
-  a.wpk = (const uint8_t*)op.w; a.bias = (const float*)op.bias; a.res = (const float*)op.aux0;
+  a.bias = (const float*)op.bias; a.res = (const float*)op.aux0;
   a.tab3 = (const float*)op.aux1; a.dst = (float*)op.dst;
   a.stats = (unsigned long long*)op.dst2;
   a.dbg = (long long*)op.aux2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.Cout = op.Cout; a.ks = op.i0; a.HW = op.H * op.W;
   a.NT = op.i1;
   MCVD_CHECK(a.NT >= 16 && a.NT <= 256 && a.NT % 16 == 0 && op.Cout % a.NT == 0,
-             "CONV_UMMA: n tile %d invalid for Cout %d", a.NT, op.Cout);
+             "CONV_UMMA2: n tile %d invalid for Cout %d", a.NT, op.Cout);
   const bool stats = a.stats != nullptr;
   const int KB = plan_kb(op.H, op.W, op.i0, a.C0, a.C1, a.C2, a.C3, a.NT, stats);
-  MCVD_CHECK(KB != 0, "CONV_UMMA: channels (%d,%d | %d,%d) must be multiples of 16 and the %dx%d slab must fit",
+  MCVD_CHECK(KB != 0, "CONV_UMMA2: channels (%d,%d | %d,%d) must be multiples of 16 and the %dx%d slab must fit",
              a.C0, a.C1, a.C2, a.C3, op.H, op.W);
-  MCVD_CHECK(op.i2 == 0 || op.i2 == KB, "CONV_UMMA: weights were packed for K-block %d, the plan says %d", op.i2, KB);
+  MCVD_CHECK(op.i2 == 0 || op.i2 == KB, "CONV_UMMA2: weights were packed for K-block %d, the plan says %d", op.i2, KB);
   Plan p;
   make_plan(op.H, op.W, op.i0, a.C0, a.C1, a.C2, a.C3, a.NT, KB, stats, p);
-  a.KB = KB; a.HP = p.HP; a.halo0 = p.halo0; a.NB = p.NB; a.SA = p.SA; a.R = p.R; a.NJ = p.NJ;
-  a.Wp = p.Wp; a.Pimg = p.Pimg; a.tmem_cols = p.tmem_cols;
+  a.KB = KB; a.HP = p.HP; a.halo0 = p.halo0; a.NB = p.NB; a.SA = p.SA; a.R = p.R; a.NJ = p.NJ; a.J = p.J;
+  a.nsets = p.nsets; a.Wp = p.Wp; a.Pimg = p.Pimg; a.tmem_cols = p.tmem_cols;
   a.off_img = p.off_img; a.off_raw = p.off_raw; a.off_b = p.off_b; a.off_pad = p.off_pad; a.off_row = p.off_row;
   a.off_stat = p.off_stat; a.off_bias = p.off_bias; a.off_bar = p.off_bar;
-  a.a_plane = p.a_plane; a.raw_stage = p.raw_stage; a.b_stage = p.b_stage;
+  a.a_plane = p.a_plane; a.raw_stage = p.raw_stage; a.b_stage = p.b_stage; a.b_rows = p.b_stage / 512;
   a.Qtot = (long long)op.B * a.Pimg;
-  MCVD_CHECK((long long)op.B * op.H * op.W < (1LL << 31) && a.Qtot < (1LL << 31), "CONV_UMMA: too many pixels");
-  MCVD_CHECK(!stats || a.Pimg >= 64, "CONV_UMMA: epilogue statistics need images of >= 64 positions");
+  MCVD_CHECK((long long)op.B * op.H * op.W < (1LL << 31) && a.Qtot < (1LL << 31), "CONV_UMMA2: too many pixels");
+  MCVD_CHECK(!stats || a.Pimg >= 64, "CONV_UMMA2: epilogue statistics need images of >= 64 positions");
   a.nKB0 = (a.C0 + a.C1) / KB;
   a.nKB = a.nKB0 + (a.C2 + a.C3) / KB;
   a.act_in = (op.flags & MCVD_F_ACT_IN) ? 1 : 0;
@@ -759,20 +802,40 @@ int launch_conv_umma2(const McvdOp& op, cudaStream_t s) {
   a.wscale = op.f1; a.oscale = op.f0;
   a.dbgf = op.i7;
   a.tiles_n = op.Cout / a.NT;
-  const long long pairs_m = (a.Qtot + 2 * MT - 1) / (2 * MT);
-  a.nunits = (int)(pairs_m * a.tiles_n);
+  a.PT = (int)((a.Qtot + 2 * MT - 1) / (2 * MT));
+  a.njobs = a.PT * a.tiles_n;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int ncl = sms / 2;
-  if (a.nunits < ncl) ncl = a.nunits;
+  if (a.njobs < ncl) ncl = a.njobs;
+  // weight tensor map: the packed stage images as rows of 512 bytes (64 x u64), one box = one stage of one CTA
+  EncodeTiledFn enc = encode_tiled();
+  MCVD_CHECK(enc != nullptr, "CONV_UMMA2: cuTensorMapEncodeTiled is not available from this driver");
+  const int taps = a.ks * a.ks;
+  const long long per_unit = (long long)a.nKB0 * taps + (a.nKB - a.nKB0);
+  const long long total_rows = per_unit * 2 * a.tiles_n * a.b_rows;
+  CUtensorMap wmap;
+  {
+    cuuint64_t gdim[2] = {64, (cuuint64_t)total_rows};
+    cuuint64_t gstride[1] = {512};
+    cuuint32_t box[2] = {64, a.b_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&wmap, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void*>(op.w), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MCVD_CHECK(r == CUDA_SUCCESS, "CONV_UMMA2: cuTensorMapEncodeTiled failed (%d) for %lld rows of 512 B, box %u rows",
+               (int)r, total_rows, a.b_rows);
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    MCVD_CHECK(e == cudaSuccess, "CONV_UMMA: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    MCVD_CHECK(e == cudaSuccess, "CONV_UMMA2: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  k_conv_umma2<<<2 * ncl, NTHREADS, p.smem, s>>>(a);
+  if (KB == 16) k_conv_umma2<1><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+  else k_conv_umma2<2><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
   MCVD_CUDA_LAUNCH_CHECK("conv_umma2");
   return 0;
 }
@@ -783,8 +846,8 @@ extern "C" int mcvd_umma2_plan(int H, int W, int ks, int C0, int C1, int C2, int
   return mcvd::plan_kb(H, W, ks, C0, C1, C2, C3, n_tile, stats != 0);
 }
 
-// shared-memory plan of a conv (diagnostics / tests): out[0..7] = KB, HP, image stages, raw-ring stages, weight
-// stages, image slots per tile, TMEM columns, dynamic shared memory bytes; returns 0, or -1 when nothing fits
+// shared-memory plan of a conv (diagnostics / tests): out[0..9] = KB, HP, image stages, raw-ring stages, weight
+// stages, image slots per tile, TMEM columns, dynamic shared memory bytes, tiles per unit, TMEM sets; returns 0, or -1
 extern "C" int mcvd_umma2_plan_info(int H, int W, int ks, int C0, int C1, int C2, int C3, int n_tile, int stats,
                                     int* out) {
   const int kb = mcvd::plan_kb(H, W, ks, C0, C1, C2, C3, n_tile, stats != 0);
@@ -792,7 +855,7 @@ extern "C" int mcvd_umma2_plan_info(int H, int W, int ks, int C0, int C1, int C2
   mcvd::Plan p;
   mcvd::make_plan(H, W, ks, C0, C1, C2, C3, n_tile, kb, stats != 0, p);
   out[0] = kb; out[1] = p.HP; out[2] = p.SA; out[3] = p.R; out[4] = p.NB; out[5] = p.NJ; out[6] = p.tmem_cols;
-  out[7] = (int)p.smem;
+  out[7] = (int)p.smem; out[8] = p.J; out[9] = p.nsets;
   return 0;
 }
 

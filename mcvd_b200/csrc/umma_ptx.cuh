@@ -36,6 +36,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// waiters that are not on the critical path (producers waiting for a free stage, epilogue warps waiting for an
+// accumulator, the weight loader): try_wait with an explicit suspend-time hint, so the warp is parked by the
+// hardware instead of spinning.  Without the hint try_wait returns almost immediately: 17 polling warps executed
+// 36 M TRYWAIT+BRA pairs in one conv launch and took a third of all issue slots -- away from the single MMA-issuing
+// warp (profiles/r2_ncu_conv2_polling.txt).
+__device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (!done);
+}
+// non-suspending variant: mbarrier.test_wait returns at once, the thread spins (latency-critical single pollers)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
 // named barrier over a subset of the CTA's warps (ids 1..15; 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -121,9 +155,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-// arrive on an mbarrier in another CTA of the cluster (release at cluster scope)
+// arrive on an mbarrier in another CTA of the cluster.  Default semantics (.release at CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id) does: the data this publishes is the ARRIVING CTA's own shared memory, consumed by
+// its own tensor core.  (.release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR per arrive, which also waits for the
+// thread's cp.async prefetches in flight.)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait on a local mbarrier whose arrivals come from the peer CTA (acquire at cluster scope)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {

@@ -169,7 +169,19 @@ def umma2_stats_bytes(B: int, H: int, W: int, ks: int, cout: int) -> int:
 
 def umma2_plan_info(H, W, ks, c0, c1, c2, c3, n_tile, stats):
     """dict of the shared-memory plan (K-block, slab rows, ring depths, bytes) or None"""
-    out = (C.c_int * 8)()
+    out = (C.c_int * 10)()
     if load().mcvd_umma2_plan_info(H, W, ks, c0, c1, c2, c3, n_tile, 1 if stats else 0, out) != 0:
         return None
-    return dict(zip(("kb", "hp", "sa", "r", "nb", "nj", "tmem_cols", "smem"), list(out)))
+    return dict(zip(("kb", "hp", "sa", "r", "nb", "nj", "tmem_cols", "smem", "j", "nsets"), list(out)))
+
+
+def umma2_pick_nt(cout: int, ks: int) -> int:
+    """n tile of an OP_CONV_UMMA2 op: the largest multiple of 16 dividing Cout that is <= 128 for 3x3 convs (two or more
+    position tiles then share every weight stage, TMEM holds two accumulator sets) and <= 256 for 1x1 convs (few
+    weights; fewer n tiles mean fewer re-stagings of the input slab).  0 when Cout is not a multiple of 16."""
+    cap = 128 if ks == 3 else 256
+    best = 0
+    for d in range(16, cap + 1, 16):
+        if cout % d == 0:
+            best = d
+    return best

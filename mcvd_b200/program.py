@@ -330,6 +330,7 @@ class Engine:
             dst = f32(B, H, H, cout)
             nt = _pick_nt(cout) if cout % 16 == 0 else 0
             if self.conv_mode == "umma2" and nt:
+                nt = lib.umma2_pick_nt(cout, ks)
                 sc_src = sc_taps = None
                 c2 = c3 = 0
                 if shortcut is not None:
@@ -361,6 +362,7 @@ class Engine:
                          flags=fl, **kw2)
                     P.n_umma += 1
                     return dst
+                nt = _pick_nt(cout)
             kb = lib.umma_kblock(src.c0, src.c1) if self.conv_mode == "umma" else 0
             sc = None
             if shortcut is not None:                       # (Src, wname, bname): 1x1 Conv_2 of the skip branch

@@ -135,7 +135,7 @@ def test_conv_umma2(case):
         ref = ref + res.double()
     ref = (ref * scale).float()
 
-    nt = max(dd for dd in range(16, 257, 16) if Cout % dd == 0)
+    nt = lib.umma2_pick_nt(Cout, ks)
     pimg = (H + 1) * (H + 1) if ks == 3 else H * H
     use_stats = use_stats and pimg >= 64
     kb = lib.umma2_plan(H, H, ks, C0, C1, C2, C3, nt, use_stats)
@@ -173,7 +173,7 @@ def test_finalize_from_epilogue_statistics(B, H, C0, C1, ks0, ks1):
         Cc = xd.shape[3]
         w = torch.zeros(Cc, Cc, ks, ks)
         w[:, :, ks // 2, ks // 2] = torch.eye(Cc)
-        nt = max(dd for dd in range(16, 257, 16) if Cc % dd == 0)
+        nt = lib.umma2_pick_nt(Cc, ks)
         kb = lib.umma2_plan(H, H, ks, Cc, 0, 0, 0, nt, True)
         pk, wscale = pack2(taps_of(w).to(DEV), None, nt, kb)
         out = torch.zeros(Bn, H, H, Cc, device=DEV)

@@ -25,7 +25,7 @@ use_res = "r" in flags
 use_stats = "g" in flags
 quick = "q" in flags
 C2 = C3 = 0
-NT = max(d for d in range(16, 257, 16) if Cout % d == 0)
+NT = lib.umma2_pick_nt(Cout, ks)
 split = 3
 dbgf = 0
 for f in flags:

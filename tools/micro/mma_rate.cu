@@ -82,6 +82,33 @@ __global__ void __launch_bounds__(128, 1) k_rate(Cfg c, long long* out) {
             mma(d1, ah, bh); mma(d1, al, bh); mma(d1, ah, bl);
           }
         }
+      } else if (c.pattern == 6 || c.pattern == 7) {
+        // the conv kernel's exact operand geometry (KB = 16, HP = 260, two tiles per unit, 16 weight stages of
+        // 32*N bytes, 4 accumulators), no barriers: pattern 6 with the per-tap commit, 7 without
+        const int HPk = 260;
+        const uint32_t a_plane16 = 2 * HPk, a_stage16 = 2 * a_plane16, b_stage16 = (32u * c.N) >> 4, b_lo16 = (16u * c.N) >> 4;
+        const uint64_t ap = make_desc_sw(a0 + 66 * 16, HPk * 16, 128, 0), bp = make_desc_sw(b0, nb * 16, 128, 0);
+        const uint32_t cb = smem_u32(&bar2);
+        int bst = 0, ast = 0, unit = 0;
+        for (int it = 0; it < c.iters; it += 54) {          // one K-block: 9 taps x 2 tiles x 3 MMAs
+          const uint32_t dset = tm + (uint32_t)((unit & 1) * 2 * c.N);
+          int dy = -1, dx = -1;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t sh = (uint64_t)(int64_t)(dy * 65 + dx);
+            const uint64_t bh = bp + (uint64_t)(bst * b_stage16), bl = bh + b_lo16;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t ah_ = ap + (uint64_t)(((ast + j) & 3) * a_stage16) + sh, al_ = ah_ + a_plane16;
+              const uint32_t d = dset + (uint32_t)(j * c.N);
+              mma(d, ah_, bh); mma(d, al_, bh); mma(d, ah_, bl);
+            }
+            if (c.pattern == 6) umma2_commit_mc(cb);
+            if (++bst == 16) bst = 0;
+            if (++dx == 2) { dx = -1; ++dy; }
+          }
+          ast = (ast + 2) & 3;
+          if ((it / 54) % 6 == 5) ++unit;
+        }
       } else if (c.pattern >= 3) {                // 6 MMAs + one commit per "tap" (the conv kernel's stage release)
         const uint32_t cb = smem_u32(&bar2);
         const uint32_t cb_remote = CG == 2 ? mapa_u32(cb, 1) : cb;
@@ -129,12 +156,13 @@ int main() {
   printf("cycles per tcgen05.mma (K=16, fp16), mean over issuing CTAs; ideal tensor time = M*N/ (128*2) per SM = N/2 (M=128 per SM)\n");
   for (int swz = 0; swz < 2; ++swz)
     for (int cg = 1; cg <= 2; ++cg)
-      for (int pattern = (swz ? 6 : 0); pattern < 6; ++pattern)
+      for (int pattern = (swz ? 8 : 5); pattern < 8; ++pattern)
         for (int nacc = 1; nacc <= (pattern < 3 ? 2 : 1); ++nacc)
           for (int N : Ns) {
             if (nacc * N > 512) continue;
             if (cg == 1 && pattern > 3) continue;
-            Cfg c{cg, N, swz, nacc, pattern, 1800};
+            if (pattern >= 6 && 4 * N > 512) continue;
+            Cfg c{cg, N, swz, nacc, pattern, 1782};
             const int mmas = c.iters * (pattern == 0 ? 1 : 3);
             cudaMemset(out, 0, 148 * sizeof(long long));
             for (int rep = 0; rep < 2; ++rep) {
