@@ -36,8 +36,8 @@
 //     128-byte-line stores, optional exact integer GroupNorm partial sums of the stored output (fixed point
 //     2^-16, order-independent => bit-exact under clip sharding), which replaces the k_gn_partial pass.
 //
-// Warp roles (608 threads, one CTA per SM, clusters of 2):
-//   warps 0-8 producers | 9 weight loader (TMA) | 10 MMA issuer (leader CTA only) | 11-18 epilogue
+// Warp roles (640 threads, one CTA per SM, clusters of 2):
+//   warps 0-8 producers | 9 weight loader (TMA) | 10-11 MMA issuers (leader CTA only) | 12-19 epilogue
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -53,10 +53,11 @@ using namespace ptx;
 constexpr int NPROD = 288;
 constexpr int NPW = NPROD / 32;
 constexpr int W_LOAD = 9;
-constexpr int W_MMA = 10;
-constexpr int W_EPI = 11;
+constexpr int W_MMA = 10;               // two MMA-issuing warps (10, 11): warp m issues for position tiles j = m, m+2
+constexpr int NMMA_W = 2;
+constexpr int W_EPI = 12;
 constexpr int NEPI_W = 8;
-constexpr int NTHREADS = (W_EPI + NEPI_W) * 32;      // 608
+constexpr int NTHREADS = (W_EPI + NEPI_W) * 32;      // 640
 constexpr int MT = 128;                 // positions per CTA and tile
 constexpr int JMAX = 4;                 // position tiles per unit (accumulators per TMEM set)
 constexpr float STAT_SCALE = 65536.0f;  // fixed-point scale of the epilogue statistics
@@ -85,10 +86,12 @@ struct C2Args {
   uint32_t a_plane, raw_stage, b_stage, b_rows;      // b_rows = 512-byte rows of the weight tensor map per stage
 };
 
-// flat position -> pixel index (b*H + y)*W + x or -1 (padding / out of range)
-__device__ __forceinline__ int decode_pos(const C2Args& a, long long q) {
+// flat position -> pixel index (b*H + y)*W + x or -1 (padding / out of range); b_out = image of the position
+__device__ __forceinline__ int decode_pos(const C2Args& a, long long q, int& b_out) {
+  b_out = 0;
   if (q < 0 || q >= a.Qtot) return -1;
   const int b = (int)(q / a.Pimg);
+  b_out = b;
   const int r = (int)(q - (long long)b * a.Pimg);
   const int rr = r / a.Wp, cc = r - rr * a.Wp;
   if (a.ks == 3) {
@@ -140,7 +143,7 @@ struct Units {
   }
 };
 
-template <int KSTEPS>      // k16 steps per K-block: 1 (KB = 16) or 2 (KB = 32)
+template <int KSTEPS, bool DBGC>      // k16 steps per K-block: 1 (KB = 16) or 2 (KB = 32); cycle counters compiled in
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -154,7 +157,7 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };                       // 2 * NPW warp arrivals (local + peer)
   auto A_EMPTY = [&](int i) { return bar0 + 8u * (SA + i); };               // tcgen05.commit, multicast
   auto B_FULL = [&](int i) { return bar0 + 8u * (2 * SA + i); };            // expect_tx (leader) + TMA bytes of both CTAs
-  auto B_EMPTY = [&](int i) { return bar0 + 8u * (2 * SA + NB + i); };      // tcgen05.commit, multicast
+  auto B_EMPTY = [&](int i) { return bar0 + 8u * (2 * SA + NB + i); };      // one tcgen05.commit (multicast) per MMA warp
   auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * SA + 2 * NB + i); };             // [set*JMAX + j], commit mc
   auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * SA + 2 * NB + 2 * JMAX + i); }; // 8 warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + a.off_bar + 8 * (2 * SA + 2 * NB + 4 * JMAX));
@@ -162,7 +165,7 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
 
   if (tid == 0) {
     for (int i = 0; i < SA; ++i) { mbar_init(A_FULL(i), 2 * NPW); mbar_init(A_EMPTY(i), 1); }
-    for (int i = 0; i < NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), NMMA_W); }
     for (int i = 0; i < 2 * JMAX; ++i) { mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 8); }
     fence_barrier_init();
   }
@@ -176,10 +179,10 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
+  long long* dbg = (DBGC && a.dbg) ? a.dbg + (size_t)blockIdx.x * 16 : nullptr;
   const long long t_begin = dbg ? clock64() : 0;
-#define DBG_T(var) long long var = dbg ? clock64() : 0
-#define DBG_ADD(slot, since, cond) do { if (dbg && (cond)) { long long t__ = clock64(); dbg[slot] += t__ - since; since = t__; } } while (0)
+#define DBG_T(var) long long var = (DBGC && dbg) ? clock64() : 0
+#define DBG_ADD(slot, since, cond) do { if (DBGC && dbg && (cond)) { long long t__ = clock64(); dbg[slot] += t__ - since; since = t__; } } while (0)
 
   if (warp < W_LOAD) {
     // =============================== producers ===============================
@@ -193,7 +196,8 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
     const int RPP = NPROD >> pj_shift;                         // rows per pass: 36 or 72
     const int Cin = a.C0 + a.C1;
     const uint32_t raw0 = sbase + a.off_raw, img0 = sbase + a.off_img;
-    int* rowinfo = reinterpret_cast<int*>(smem + a.off_row);     // [2 (unit parity)][J][HP] pixel index or -1
+    int* rowinfo = reinterpret_cast<int*>(smem + a.off_row);     // [2 (unit parity)][J][HP] pixel | image << 24, or -1
+    int* tile_b0 = rowinfo + 2 * a.J * a.HP;                     // [2][J] first image of each slab
     const uint32_t a_full_leader = mapa_u32(A_FULL(0), 0);
     const int Rm1 = a.R - 1;
 
@@ -230,7 +234,12 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
           for (int x = tid; x < i_cnt * a.HP; x += NPROD) {
             const int jj = x / a.HP, h = x - jj * a.HP;
             const long long p0 = (long long)(i_pt0 + jj) * (2 * MT) + (long long)rank * MT - a.halo0;
-            rowinfo[(i_par * a.J + jj) * a.HP + h] = decode_pos(a, p0 + h);
+            const int b_first = p0 <= 0 ? 0 : (int)min((long long)(a.B - 1), p0 / a.Pimg);   // image of the slab's first row
+            int b;
+            const int pix = decode_pos(a, p0 + h, b);
+            // pixel index (< 2^24, checked by the launcher) | image relative to the slab's first one << 24
+            rowinfo[(i_par * a.J + jj) * a.HP + h] = pix < 0 ? -1 : (pix | ((b - b_first) << 24));
+            if (h == 0) tile_b0[i_par * a.J + jj] = b_first;
           }
           named_bar_sync(1, NPROD);
           i_new = false;
@@ -245,11 +254,12 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
         const float* sj = src + cc0 + j16 * 4;
         const int* ri = rowinfo + (i_par * a.J + i_j) * a.HP;
         if (!(a.dbgf & 1)) {
+#pragma unroll 2
           for (int h = hrow; h < hhi; h += RPP) {
             if (h < hlo) continue;
-            const int pix = ri[h];
-            const float* p = pix >= 0 ? sj + (long long)pix * cs : src;
-            cp_async16(rst + (uint32_t)((h << pj_shift) + j16) * 16u, p, pix >= 0 ? 16u : 0u);
+            const int info = ri[h];
+            const float* p = info >= 0 ? sj + (long long)(info & 0xffffff) * cs : src;
+            cp_async16(rst + (uint32_t)((h << pj_shift) + j16) * 16u, p, info >= 0 ? 16u : 0u);
           }
         }
         if (++i_j == i_cnt) {
@@ -261,6 +271,21 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
       // ---- transform job it - (R-1) ----
       const int gt = it - Rm1;
       if (gt < 0) continue;
+      // norm table of this job's K-block for the slab's first image: requested now, so the L2 round trip of the three
+      // loads overlaps the waits below (every job reads other channels, so they always miss L1)
+      const bool seg1 = t_kb >= a.nKB0;
+      const bool norm = a.tab3 != nullptr && !seg1;
+      const float* tabc = a.tab3 + t_kb * a.KB + j16 * 4;
+      const int b0_tile = tile_b0[t_par * a.J + t_j];
+      float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), tg = tm, ts = tm;
+      int tb_img = -1;
+      if (norm && !(a.dbgf & 1)) {
+        const float* tb = tabc + (long long)b0_tile * 3 * Cin;
+        tm = __ldg(reinterpret_cast<const float4*>(tb));
+        tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
+        ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
+        tb_img = b0_tile;
+      }
       if (Rm1 == 1) cp_async_wait<1>(); else if (Rm1 == 2) cp_async_wait<2>(); else cp_async_wait<3>();
       const int st = gt % SA;
       DBG_T(tp);
@@ -268,49 +293,57 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
       if (lane == 0) { if (a.dbgf & 8) mbar_wait(A_EMPTY(st), ((gt / SA) & 1) ^ 1); else mbar_wait_parked(A_EMPTY(st), ((gt / SA) & 1) ^ 1); }
       __syncwarp();
       DBG_ADD(1, tp, tid == 0);
-      const bool seg1 = t_kb >= a.nKB0;
-      const bool norm = a.tab3 != nullptr && !seg1;
       const int hlo = seg1 ? a.halo0 : 0, hhi = seg1 ? a.halo0 + MT : a.HP;
       const uint32_t rst = raw0 + (uint32_t)(gt % a.R) * a.raw_stage;
       const uint32_t hi_base = img0 + (uint32_t)st * 2u * a.a_plane, lo_base = hi_base + a.a_plane;
       const uint32_t img_off = (uint32_t)(j16 >> 1) * (uint32_t)a.HP * 16u + (uint32_t)(j16 & 1) * 8u;
-      const float* tabc = a.tab3 + t_kb * a.KB + j16 * 4;
       const int* ri = rowinfo + (t_par * a.J + t_j) * a.HP;
-      // (mean, rstd*G, S) of this thread's 4 channels for the image of the current row: a slab touches one or two
-      // images on the large maps, so the three L1 loads are paid once per job, not once per row
-      float4 tm = make_float4(0.f, 0.f, 0.f, 0.f), tg = tm, ts = tm;
-      int tb_img = -1;
+      // Two slab rows per trip (independent instruction chains; more unrolling cost more in instruction-cache misses
+      // than it gained).  (mean, rstd*G, S) of this thread's 4 channels are cached for the image of the previous row:
+      // a slab touches one or two images on the large maps.
       if (!(a.dbgf & 1)) {
-#pragma unroll 4
-        for (int h = hrow; h < hhi; h += RPP) {
-          if (h < hlo) continue;
-          const int pix = ri[h];
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
-                       : "r"(rst + (uint32_t)((h << pj_shift) + j16) * 16u));
-          uint32_t h0 = 0u, h1 = 0u, l0 = 0u, l1 = 0u;
-          if (pix >= 0) {
-            float v[4] = {x.x, x.y, x.z, x.w};
-            if (norm) {
-              const int img = pix / a.HW;
-              if (img != tb_img) {
-                const float* tb = tabc + (long long)img * 3 * Cin;
-                tm = __ldg(reinterpret_cast<const float4*>(tb));
-                tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
-                ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
-                tb_img = img;
-              }
-              v[0] = fmaf(v[0] - tm.x, tg.x, ts.x); v[1] = fmaf(v[1] - tm.y, tg.y, ts.y);
-              v[2] = fmaf(v[2] - tm.z, tg.z, ts.z); v[3] = fmaf(v[3] - tm.w, tg.w, ts.w);
-              if (a.act_in) silu_fast4(v);
+#pragma unroll 1
+        for (int hb = hrow; hb < hhi; hb += 2 * RPP) {
+          int info[2];
+          float4 x[2];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int h = hb + i * RPP;
+            info[i] = -2;                                        // -2: no such row for this thread
+            if (h < hhi && h >= hlo) {
+              info[i] = ri[h];
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(x[i].x), "=f"(x[i].y), "=f"(x[i].z), "=f"(x[i].w)
+                           : "r"(rst + (uint32_t)((h << pj_shift) + j16) * 16u));
             }
-            split2_sat(v[0], v[1], h0, l0);
-            split2_sat(v[2], v[3], h1, l1);
           }
-          const uint32_t off = img_off + (uint32_t)h * 16u;
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_base + off), "r"(h0), "r"(h1) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_base + off), "r"(l0), "r"(l1) : "memory");
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (info[i] == -2) continue;
+            const int h = hb + i * RPP;
+            uint32_t h0 = 0u, h1 = 0u, l0 = 0u, l1 = 0u;
+            if (info[i] >= 0) {
+              float v[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+              if (norm) {
+                const int img = b0_tile + (info[i] >> 24);
+                if (img != tb_img) {
+                  const float* tb = tabc + (long long)img * 3 * Cin;
+                  tm = __ldg(reinterpret_cast<const float4*>(tb));
+                  tg = __ldg(reinterpret_cast<const float4*>(tb + Cin));
+                  ts = __ldg(reinterpret_cast<const float4*>(tb + 2 * Cin));
+                  tb_img = img;
+                }
+                v[0] = fmaf(v[0] - tm.x, tg.x, ts.x); v[1] = fmaf(v[1] - tm.y, tg.y, ts.y);
+                v[2] = fmaf(v[2] - tm.z, tg.z, ts.z); v[3] = fmaf(v[3] - tm.w, tg.w, ts.w);
+                if (a.act_in) silu_fast4(v);
+              }
+              split2_sat(v[0], v[1], h0, l0);
+              split2_sat(v[2], v[3], h1, l1);
+            }
+            const uint32_t off = img_off + (uint32_t)h * 16u;
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(hi_base + off), "r"(h0), "r"(h1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(lo_base + off), "r"(l0), "r"(l1) : "memory");
+          }
         }
       }
       DBG_ADD(3, tp, tid == 0);
@@ -350,26 +383,28 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
       }
     }
     __syncwarp();
-  } else if (warp == W_MMA) {
+  } else if (warp < W_EPI) {
     if (rank == 0) {
-      // =============================== MMA issuer (leader CTA) ===============================
-      // The WHOLE warp walks the loops (warp-uniform control flow and address arithmetic, which the compiler keeps
-      // on the uniform datapath); only the tcgen05.mma / tcgen05.commit instructions sit under elect.sync.  A
-      // single-thread loop with per-MMA descriptor arithmetic was issue-bound at ~150-290 cycles per MMA, 3-6x the
-      // tensor time (profiles/r2_conv2_isolation.txt).  Descriptors differ only in their low word (start address
-      // field, < 2^14 16-byte units, never carries into the LBO field).  The waits are plain (CTA-scope acquire)
-      // try_waits: an .acquire.cluster wait compiles to TRYWAIT + CCTL.IVALL (an L1 invalidation per weight stage),
-      // and nothing this thread reads afterwards needs it -- the operands are read by each SM's tensor core from
-      // its own shared memory, published by fence.proxy.async (slabs) or written by TMA (weights).
+      // =============================== MMA issuers (leader CTA) ===============================
+      // Two warps, one per position tile parity: warp m issues the MMAs of tiles j = m, m+2 (each accumulator is fed
+      // by one warp, in order), waits for its own slabs, and both commit every weight stage (B_EMPTY counts 2).  One
+      // warp alone was bound by the latency of its own instruction stream (~130 instructions / ~950 cycles per weight
+      // stage at ~7 cycles per dependent instruction, 3x the tensor time of the 6 MMAs: ncu source page in
+      // profiles/r2_ncu_conv2_polling.txt).  The whole warp walks the loops (uniform control flow); only tcgen05.mma /
+      // tcgen05.commit sit under elect.sync.  Descriptors differ only in their low word (start address field,
+      // < 2^14 16-byte units, never carries into the LBO field).  The waits are plain CTA-scope try_waits: an
+      // .acquire.cluster wait compiles to TRYWAIT + CCTL.IVALL (an L1 invalidation per stage), and nothing this thread
+      // reads afterwards needs it -- the operands are read by each SM's tensor core from its own shared memory,
+      // published by fence.proxy.async (slabs) or written by TMA (weights).
+      const int m = warp - W_MMA;
       const uint32_t idesc = make_idesc_f16(2 * MT, a.NT);
       const uint64_t a_proto = make_desc(0, (uint32_t)a.HP * 16, 128), b_proto = make_desc(0, (uint32_t)(a.NT >> 1) * 16, 128);
       const uint32_t a_hiw = (uint32_t)(a_proto >> 32), b_hiw = (uint32_t)(b_proto >> 32);
-      const uint32_t a_low = (uint32_t)a_proto, b_low = (uint32_t)b_proto;
       const uint32_t a_plane16 = a.a_plane >> 4, b_step16 = (32u * a.NT) >> 4, b_lo16 = (16u * a.NT) >> 4;
       const uint32_t a_kstep16 = 2u * (uint32_t)a.HP;
       const uint32_t a_stage16 = 2 * a_plane16, b_stage16 = a.b_stage >> 4;
-      const uint32_t a_org = a_low + ((sbase + a.off_img) >> 4) + (uint32_t)a.halo0;      // low word of stage 0, centre tap
-      const uint32_t b_org = b_low + ((sbase + a.off_b) >> 4);
+      const uint32_t a_org = (uint32_t)a_proto + ((sbase + a.off_img) >> 4) + (uint32_t)a.halo0;   // stage 0, centre tap
+      const uint32_t b_org = (uint32_t)b_proto + ((sbase + a.off_b) >> 4);
       const bool w_lo = (a.split & 2) != 0, a_lo = (a.split & 1) != 0;
       auto desc = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
       Units un(a, cid, ncl);
@@ -380,79 +415,79 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
         const int set = iu % a.nsets;
         const uint32_t acc_ph = (uint32_t)((iu / a.nsets) & 1);
         DBG_T(tm);
-        for (int j = 0; j < cnt; ++j) mbar_wait_parked(ACC_EMPTY(set * JMAX + j), acc_ph ^ 1);   // epilogues drained them
-        DBG_ADD(5, tm, lane == 0);
+        for (int j = m; j < cnt; j += NMMA_W) mbar_wait(ACC_EMPTY(set * JMAX + j), acc_ph ^ 1);   // epilogue drained it
+        DBG_ADD(5, tm, lane == 0 && m == 0);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(set * a.J * a.NT);
+        const uint32_t d_set = tmem_base + (uint32_t)(set * a.J * a.NT);
         for (int kb = 0; kb < a.nKB; ++kb) {
-          DBG_ADD(8, tm, lane == 0);
-          // the cnt slabs of this K-block: stages ast .. ast+cnt-1 (mod SA); low descriptor words per tile
-          uint32_t a_j[JMAX];
-          {
-            int st = ast;
-            uint32_t ph = aph;
+          DBG_ADD(8, tm, lane == 0 && m == 0);
+          // my (at most two) slabs of this K-block: tile j lives in stage (ast + j) mod SA
+          uint32_t a_w[2] = {0u, 0u}, d_w[2] = {0u, 0u};
+          int st_w[2] = {0, 0};
+          int nmine = 0;
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-              if (j < cnt) {
-                if (a.dbgf & 8) mbar_wait(A_FULL(st), ph); else mbar_wait_parked(A_FULL(st), ph);
-                a_j[j] = a_org + (uint32_t)st * a_stage16;
-                if (++st == SA) { st = 0; ph ^= 1; }
-              }
+          for (int q = 0; q < 2; ++q) {
+            const int j = m + q * NMMA_W;
+            if (j < cnt) {
+              int st = ast + j;
+              uint32_t ph = aph;
+              if (st >= SA) { st -= SA; ph ^= 1; }
+              mbar_wait(A_FULL(st), ph);
+              a_w[q] = a_org + (uint32_t)st * a_stage16;
+              d_w[q] = d_set + (uint32_t)(j * a.NT);
+              st_w[q] = st;
+              nmine = q + 1;
             }
           }
-          DBG_ADD(6, tm, lane == 0);
+          DBG_ADD(6, tm, lane == 0 && m == 0);
           const bool main = kb < a.nKB0;
           const int ntap = main ? taps : 1;
-          int dy = -1, dx = -1;                              // tap offsets (3x3 main segment), (0, 0) otherwise
-          if (ntap == 1) { dy = 0; dx = 0; }
+          // (no unrolling over the taps: the hot code of all roles has to stay inside the instruction cache -- with the
+          // taps unrolled the kernel ran at a 70 % i-cache hit rate and "no instruction" was the top stall reason)
+          int dy = (ntap == 1) ? 0 : -1, dx = dy;
+#pragma unroll 1
           for (int tap = 0; tap < ntap; ++tap) {
-            DBG_ADD(8, tm, lane == 0);
-            if (a.dbgf & 8) mbar_wait(B_FULL(bst), bph); else mbar_wait_parked(B_FULL(bst), bph);
-            DBG_ADD(7, tm, lane == 0);
+            DBG_ADD(8, tm, lane == 0 && m == 0);
+            mbar_wait(B_FULL(bst), bph);
+            DBG_ADD(7, tm, lane == 0 && m == 0);
             const uint32_t shift = (uint32_t)(dy * a.Wp + dx);
+            if (++dx == 2) { dx = -1; ++dy; }
             const uint32_t first = (kb > 0 || tap > 0) ? 1u : 0u;      // 0 only for the first MMA of an accumulator
             if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < JMAX; ++j) {
-                if (j < cnt) {
-                  const uint32_t d = d0 + (uint32_t)(j * a.NT);
-                  uint32_t al = a_j[j] + shift, bl = b_cur;
+              for (int q = 0; q < 2; ++q) {
+                if (q < nmine) {
+                  uint32_t al = a_w[q] + shift, bl = b_cur;
 #pragma unroll
                   for (int s = 0; s < KSTEPS; ++s) {
                     const uint64_t dah = desc(al, a_hiw), dal = desc(al + a_plane16, a_hiw);
                     const uint64_t dbh = desc(bl, b_hiw), dbl = desc(bl + b_lo16, b_hiw);
-                    umma2_f16(d, dah, dbh, idesc, (s > 0) ? 1u : first);
-                    if (a_lo) umma2_f16(d, dal, dbh, idesc, 1u);
-                    if (w_lo) umma2_f16(d, dah, dbl, idesc, 1u);
+                    umma2_f16(d_w[q], dah, dbh, idesc, (s > 0) ? 1u : first);
+                    if (a_lo) umma2_f16(d_w[q], dal, dbh, idesc, 1u);
+                    if (w_lo) umma2_f16(d_w[q], dah, dbl, idesc, 1u);
                     al += a_kstep16; bl += b_step16;
                   }
                 }
               }
-              umma2_commit_mc(B_EMPTY(bst));           // weight stage consumed (both CTAs)
+              umma2_commit_mc(B_EMPTY(bst));           // this warp is done with the weight stage (both CTAs)
             }
             __syncwarp();
             b_cur += b_stage16;
             if (++bst == NB) { bst = 0; bph ^= 1; b_cur = b_org; }
-            if (++dx == 2) { dx = -1; ++dy; }
           }
           if (elect_one()) {
-            int st = ast;
 #pragma unroll
-            for (int j = 0; j < JMAX; ++j) {
-              if (j < cnt) {
-                umma2_commit_mc(A_EMPTY(st));          // slab stages consumed (both CTAs)
-                if (++st == SA) st = 0;
-              }
-            }
+            for (int q = 0; q < 2; ++q)
+              if (q < nmine) umma2_commit_mc(A_EMPTY(st_w[q]));     // slab stages consumed (both CTAs)
           }
           __syncwarp();
           ast += cnt;
           if (ast >= SA) { ast -= SA; aph ^= 1; }
         }
         if (elect_one())
-          for (int j = 0; j < cnt; ++j) umma2_commit_mc(ACC_FULL(set * JMAX + j));
+          for (int j = m; j < cnt; j += NMMA_W) umma2_commit_mc(ACC_FULL(set * JMAX + j));
         __syncwarp();
-        DBG_ADD(8, tm, lane == 0);
+        DBG_ADD(8, tm, lane == 0 && m == 0);
         ++iu;
       }
     }
@@ -485,15 +520,13 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
         named_bar_sync(bar_id, 128);                                         // previous tile's readers are done
         for (int i = et; i < a.NT; i += 128) bias_s[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
         named_bar_sync(bar_id, 128);
-        const int mypix = decode_pos(a, p0 + lq * 32 + lane);
+        int myb;
+        const int mypix = decode_pos(a, p0 + lq * 32 + lane, myb);
         const int tile_b0 = (int)min((long long)(a.B - 1), p0 / a.Pimg);
-        const int myj = mypix >= 0 ? mypix / a.HW - tile_b0 : -1;              // image slot of this row (stats)
-        int px8[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) px8[k] = __shfl_sync(0xffffffffu, mypix, k * 4 + (lane >> 3));
+        const int myj = mypix >= 0 ? myb - tile_b0 : -1;                       // image slot of this row (stats)
         unsigned jmask = 0;                                                   // image slots present in this warp's rows
         if (a.stats) {
-#pragma unroll
+#pragma unroll 1
           for (int jj = 0; jj < 4; ++jj)
             if (__ballot_sync(0xffffffffu, myj == jj)) jmask |= 1u << jj;
         }
@@ -503,16 +536,11 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
         DBG_ADD(9, te, et == 0);
         tc_fence_after();
         const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)((set * a.J + j) * a.NT);
+#pragma unroll 1
         for (int blk = 0; blk < nblk; ++blk) {
           const int cb = blk * 32;
           const int w = min(32, a.NT - cb);
           const bool wide = (w == 32);
-          float4 rres[8];
-          if (resp && wide && !(a.dbgf & 2)) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (px8[k] >= 0) rres[k] = ld_nc_na(resp + (long long)px8[k] * a.Cout + n0 + cb + (lane & 7) * 4);
-          }
           uint32_t r[32];
           tmem_ld16(trow0 + (uint32_t)cb, r);
           if (wide) tmem_ld16(trow0 + (uint32_t)(cb + 16), r + 16);
@@ -533,28 +561,35 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
                   make_float4(__uint_as_float(r[4 * q]) * a.wscale, __uint_as_float(r[4 * q + 1]) * a.wscale,
                               __uint_as_float(r[4 * q + 2]) * a.wscale, __uint_as_float(r[4 * q + 3]) * a.wscale);
           __syncwarp();
-          // transposed phase: 8 lanes per row (32-wide block) or 4 lanes per row (16-wide tail)
+          // transposed phase: 8 lanes per row (32-wide block) or 4 lanes per row (16-wide tail); two rows per trip.
+          // Loops are kept rolled on purpose (instruction-cache footprint).
           const int lpr = wide ? 8 : 4;
           const int qc = lane & (lpr - 1), rsub = wide ? (lane >> 3) : (lane >> 2);
           const int rpi = wide ? 4 : 8;                       // rows per instruction
-          const int nk = wide ? 8 : 4;
           const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + qc * 4);
+#pragma unroll 1
+          for (int r0 = rsub; r0 < 32; r0 += 2 * rpi) {
+            float4 v[2], rv[2];
+            int px[2];
+            long long off[2];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (k < nk) {
-              const int row = k * rpi + rsub;
-              const int px = wide ? px8[k] : __shfl_sync(0xffffffffu, mypix, row);
-              float4 v = pad[row * 8 + (qc ^ (row & 7))];
-              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-              const long long off = (long long)px * a.Cout + n0 + cb + qc * 4;
-              if (resp && px >= 0) {
-                const float4 rv = wide ? rres[k] : ld_nc_na(resp + off);
-                v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-              }
-              v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
-              if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-              if (px >= 0) *reinterpret_cast<float4*>(dstp + off) = v;
-              if (a.stats) pad[row * 8 + (qc ^ (row & 7))] = v;      // same thread re-reads it below
+            for (int u = 0; u < 2; ++u) {
+              const int row = r0 + u * rpi;
+              px[u] = __shfl_sync(0xffffffffu, mypix, row);
+              off[u] = (long long)px[u] * a.Cout + n0 + cb + qc * 4;
+              rv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (resp && px[u] >= 0) rv[u] = ld_nc_na(resp + off[u]);
+              v[u] = pad[row * 8 + (qc ^ (row & 7))];
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int row = r0 + u * rpi;
+              float4 t = v[u];
+              t.x = (t.x + bv.x + rv[u].x) * a.oscale; t.y = (t.y + bv.y + rv[u].y) * a.oscale;
+              t.z = (t.z + bv.z + rv[u].z) * a.oscale; t.w = (t.w + bv.w + rv[u].w) * a.oscale;
+              if (a.act_out) { t.x = silu_fast(t.x); t.y = silu_fast(t.y); t.z = silu_fast(t.z); t.w = silu_fast(t.w); }
+              if (px[u] >= 0) *reinterpret_cast<float4*>(dstp + off[u]) = t;
+              if (a.stats) pad[row * 8 + (qc ^ (row & 7))] = t;      // same thread re-reads it below
             }
           }
           if (a.stats) {
@@ -563,19 +598,16 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
               if (!(jmask & (1u << jj))) continue;
               long long s1[4] = {0, 0, 0, 0};
               unsigned long long s2[4] = {0, 0, 0, 0};
+#pragma unroll 2
+              for (int row = rsub; row < 32; row += rpi) {
+                if (__shfl_sync(0xffffffffu, myj, row) == jj) {
+                  const float4 t = pad[row * 8 + (qc ^ (row & 7))];
+                  const float f[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                if (k < nk) {
-                  const int row = k * rpi + rsub;
-                  if (__shfl_sync(0xffffffffu, myj, row) == jj) {
-                    const float4 v = pad[row * 8 + (qc ^ (row & 7))];
-                    const float f[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const int xi = __float2int_rn(f[e] * STAT_SCALE);       // saturates at +-2^31
-                      s1[e] += xi;
-                      s2[e] += (unsigned long long)((long long)xi * (long long)xi);
-                    }
+                  for (int e = 0; e < 4; ++e) {
+                    const int xi = __float2int_rn(f[e] * STAT_SCALE);       // saturates at +-2^31
+                    s1[e] += xi;
+                    s2[e] += (unsigned long long)((long long)xi * (long long)xi);
                   }
                 }
               }
@@ -690,7 +722,7 @@ bool make_plan(int H, int W, int ks, int C0, int C1, int C2, int C3, int NT, int
   p.nsets = (2 * J * NT <= 512) ? 2 : 1;
   const int nKB0 = (C0 + C1) / KB, nKB = nKB0 + (C2 + C3) / KB;
   const size_t stat_bytes = stats ? (size_t)2 * p.NJ * 2 * NT * 8 : 0;
-  const size_t row_bytes = (size_t)2 * J * hp * 4;
+  const size_t row_bytes = (size_t)2 * J * hp * 4 + 2 * JMAX * 4;
   const size_t fixed = (size_t)NEPI_W * 4096 + row_bytes + stat_bytes + 2 * 1024 + 1024;
   const size_t limit = 227 * 1024;
   const size_t a_stage = 2 * (size_t)p.a_plane;
@@ -791,7 +823,8 @@ int launch_conv_umma2(const McvdOp& op, cudaStream_t s) {
   a.off_stat = p.off_stat; a.off_bias = p.off_bias; a.off_bar = p.off_bar;
   a.a_plane = p.a_plane; a.raw_stage = p.raw_stage; a.b_stage = p.b_stage; a.b_rows = p.b_stage / 512;
   a.Qtot = (long long)op.B * a.Pimg;
-  MCVD_CHECK((long long)op.B * op.H * op.W < (1LL << 31) && a.Qtot < (1LL << 31), "CONV_UMMA2: too many pixels");
+  MCVD_CHECK((long long)op.B * op.H * op.W <= (1LL << 24) && a.Qtot < (1LL << 31),
+             "CONV_UMMA2: more than 2^24 pixels per launch (B*H*W = %lld); split the batch", (long long)op.B * op.H * op.W);
   MCVD_CHECK(!stats || a.Pimg >= 64, "CONV_UMMA2: epilogue statistics need images of >= 64 positions");
   a.nKB0 = (a.C0 + a.C1) / KB;
   a.nKB = a.nKB0 + (a.C2 + a.C3) / KB;
@@ -829,13 +862,21 @@ int launch_conv_umma2(const McvdOp& op, cudaStream_t s) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_conv_umma2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_conv_umma2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_conv_umma2<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     MCVD_CHECK(e == cudaSuccess, "CONV_UMMA2: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  if (KB == 16) k_conv_umma2<1><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
-  else k_conv_umma2<2><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+  const bool dbgc = a.dbg != nullptr;
+  if (KB == 16) {
+    if (dbgc) k_conv_umma2<1, true><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+    else k_conv_umma2<1, false><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+  } else {
+    if (dbgc) k_conv_umma2<2, true><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+    else k_conv_umma2<2, false><<<2 * ncl, NTHREADS, p.smem, s>>>(a, wmap);
+  }
   MCVD_CUDA_LAUNCH_CHECK("conv_umma2");
   return 0;
 }
