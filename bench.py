@@ -6,9 +6,15 @@
 
 One "step" = one full reverse-diffusion pass over one batch of clips: L network evaluations + the
 final denoise evaluation + L fused updates (models/__init__.py:207-340 in the reference), i.e. one
-``ddpm_sampler`` call; it produces B * num_frames frames.  Default workload = BASELINE.json configs[1]
-("cfg2": smmnist_DDPM_big5 + ngf=96, batch 64, subsample 100, 64x64x1, concat conditioning).
-Multi-GPU = weak scaling: every rank owns ``batch`` clips (clip-sharded, no data-path collective).
+``ddpm_sampler`` call; it produces B * num_frames frames.  With ``--ar`` a step is the whole autoregressive
+``video_gen`` loop of the reference (runners/ncsn_runner.py:1501-1570): ceil(num_frames_pred / num_frames) sampler
+calls with the sliding conditioning window, num_frames_pred kept frames per clip.
+Default workload = BASELINE.json configs[1] ("cfg2": smmnist_DDPM_big5 + ngf=96, batch 64, subsample 100,
+64x64x1, concat conditioning).
+Multi-GPU: every rank owns its OWN clips (global clip ids, distinct synthetic data, noise keyed by the global
+clip id), no data-path collective, and ONE NCCL all-gather of the finished frames, which is inside the e2e timed
+region together with the host<->device copies.  ``--scaling weak`` (default): ``batch`` clips per GPU;
+``--scaling strong``: the workload's batch split over the GPUs (BASELINE: cfg4 on 4, cfg5 on 8).
 
 Prints ONE JSON line on rank 0 (see the keys at the bottom).
 """
@@ -58,7 +64,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-psnr", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--conv", default=None, choices=[None, "umma", "simt"])
+    ap.add_argument("--conv", default=None, choices=[None, "umma", "umma2", "simt"])
+    ap.add_argument("--ar", action="store_true", help="time the full autoregressive video_gen loop (num_frames_pred frames)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-batch", type=int, default=2)
     ap.add_argument("--psnr-steps", type=int, default=0, help="DDPM steps of the PSNR check (default: the workload's)")
     return ap.parse_args()
@@ -146,44 +154,121 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_forward_rate(cfg, sd, B_cpu, n_fwd=2):
-    """frames/s of the reference algorithm (oracle port) on the host cores, from timed forwards."""
-    from oracle import mcvd_oracle as O
-    torch.set_num_threads(cpu_threads())
-    x, cond = detfill.synthetic_inputs(cfg, B_cpu)
-    t = torch.full((B_cpu,), 500, dtype=torch.long)
-    O.unet_forward(cfg, sd, x, t, cond)                    # warm-up
-    t0 = time.perf_counter()
-    for _ in range(n_fwd):
-        O.unet_forward(cfg, sd, x, t, cond)
-    dt = (time.perf_counter() - t0) / n_fwd
-    L = cfg.sampling.subsample
-    frames = B_cpu * cfg.data.num_frames
-    return frames / (dt * (L + 1)), dt
+def _reference_root():
+    """The unmodified reference tree, when one is reachable on this box (it is not shipped to the GPU boxes)."""
+    for c in (os.environ.get("MCVD_REFERENCE_ROOT"), "/root/reference", os.path.join(ROOT, "baseline", "_ref")):
+        if c and os.path.exists(os.path.join(c, "models", "better", "ncsnpp_more.py")):
+            return c
+    return None
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path: the UNMODIFIED reference (``UNetMore_DDPM`` +
+    ``ddpm_sampler``, models/better/ncsnpp_more.py:721-770, models/__init__.py:207-340) imported in place when its
+    tree is reachable, else the oracle port of the same algorithm (oracle/mcvd_oracle.py, pinned to the reference).
+    One timed step = ONE FULL L-step sampler call (+ denoise) on ``batch`` clips -- no extrapolation."""
+
+    def __init__(self, cfg, workload, batch):
+        from mcvd_b200.synthetic import make_module
+        self.cfg, self.B = cfg, batch
+        _, _, self.sd = make_module(workload, "cpu")
+        self.x, self.cond = detfill.synthetic_inputs(cfg, batch)
+        self.L = cfg.sampling.subsample
+        root = _reference_root()
+        self.kind = "port"
+        self.ref_net = None
+        if root is not None:
+            try:
+                os.environ["MCVD_REFERENCE_ROOT"] = root
+                from oracle import ref_import
+                if ref_import.available():
+                    net = ref_import.build_reference_net(cfg)
+                    net.load_state_dict(self.sd, strict=False)
+                    self.ref_net, self.ref_sampler, self.kind = net.eval(), ref_import.ref_models()[1], "reference"
+            except Exception as e:                               # any import problem: the port is always there
+                log(f"reference tree at {root} not usable ({type(e).__name__}: {e}); timing the oracle port")
+        self.threads, self.thread_scan = self._pick_threads()
+
+    def forward(self):
+        t = torch.full((self.B,), 500, dtype=torch.long)
+        with torch.no_grad():
+            if self.ref_net is not None:
+                return self.ref_net(self.x, t, cond=self.cond)
+            from oracle import mcvd_oracle as O
+            return O.unet_forward(self.cfg, self.sd, self.x, t, self.cond)
+
+    def _pick_threads(self):
+        """oneDNN convolutions at batch 1-2 stop scaling well before 128 threads on the GPU hosts (and get slower):
+        time one forward at a few thread counts and keep the fastest."""
+        if os.environ.get("MCVD_CPU_THREADS"):
+            n = int(os.environ["MCVD_CPU_THREADS"])
+            torch.set_num_threads(n)
+            return n, {}
+        ncpu = os.cpu_count() or 1
+        scan = {}
+        self_threads = sorted({min(ncpu, 16), min(ncpu, 32), min(ncpu, 64), ncpu})
+        for n in self_threads:
+            torch.set_num_threads(n)
+            self.forward()
+            t0 = time.perf_counter()
+            self.forward()
+            scan[n] = time.perf_counter() - t0
+        best = min(scan, key=scan.get)
+        torch.set_num_threads(best)
+        return best, {str(k): round(v, 3) for k, v in scan.items()}
+
+    def sample(self):
+        """one full sampler call; returns seconds"""
+        torch.manual_seed(1234)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.ref_net is not None:
+                self.ref_sampler(self.x.clone(), self.ref_net, cond=self.cond, final_only=True, denoise=True,
+                                 subsample_steps=self.L, clip_before=True, verbose=False, log=False)
+            else:
+                from oracle import mcvd_oracle as O
+                fn = lambda xx, tt, cc: O.unet_forward(self.cfg, self.sd, xx, tt, cc)
+                O.ddpm_sample(fn, O.make_schedule(self.cfg), self.x.clone(), self.cond, self.L, True, True)
+        return time.perf_counter() - t0
+
+    def describe(self, dt):
+        import platform
+        cpu = platform.processor() or "unknown CPU"
+        try:
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("model name"):
+                    cpu = line.split(":", 1)[1].strip()
+                    break
+        except OSError:
+            pass
+        impl = ("unmodified reference UNetMore_DDPM + ddpm_sampler" if self.kind == "reference"
+                else "oracle port of the reference (oracle/mcvd_oracle.py)")
+        return (f"each step = one full {self.L}-step DDPM sampler call (+ denoise) of the {impl} on {self.B} clip(s) "
+                f"({dt:.1f} s), {self.threads} threads of {os.cpu_count()} on {cpu}; threads picked from one forward at "
+                f"each of {self.thread_scan}")
 
 
 def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from mcvd_b200.synthetic import make_module
-    _, net, sd = make_module(args.workload, "cpu")
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, dt = cpu_forward_rate(cfg, sd, args.cpu_batch, n_fwd=1)
-        if i >= args.warmup:
-            vals.append((v, dt))
-    v = statistics.mean(x[0] for x in vals)
-    dt = statistics.mean(x[1] for x in vals)
-    L = cfg.sampling.subsample
-    sample = (f"each step = 1 forward of the oracle port at batch {args.cpu_batch} ({dt:.2f} s), "
-              f"extrapolated x{L + 1} network calls per {args.cpu_batch * cfg.data.num_frames} frames")
+    arm = CpuArm(cfg, args.workload, args.cpu_batch)
+    log(f"CPU arm: {arm.kind}, {arm.threads} threads, scan {arm.thread_scan}")
+    for i in range(args.warmup):
+        arm.forward()                                            # warm-up steps are single forwards (allocator, oneDNN)
+    dts = [arm.sample() for _ in range(args.steps)]
+    dt = statistics.mean(dts)
+    frames = args.cpu_batch * cfg.data.num_frames
+    v = frames / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * (L + 1) * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {describe(cfg)}", "cpu_batch": args.cpu_batch},
-            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample},
+            "config": {"workload": f"{args.workload}: {describe(cfg)}", "clips_per_step": args.cpu_batch,
+                       "note": "same network, sampler, steps and frame counts as the GPU arm; the CPU arm runs "
+                               f"{args.cpu_batch} clip(s) per step instead of {cfg.bench_batch} (a 64-clip CPU step takes "
+                               "tens of minutes); frames/s is per-clip work either way"},
+            "cpu_baseline": {"value": v, "unit": "frames/s", "cores": arm.threads, "kind": arm.kind,
+                             "sample": arm.describe(dt)},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -222,26 +307,48 @@ def main():
     cfg, net, sd = make_module(args.workload, dev)
     if args.subsample:
         cfg.sampling.subsample = args.subsample
-    B = args.batch or cfg.bench_batch
     L = cfg.sampling.subsample
-    F = cfg.data.num_frames
-    lo = rank * B                                            # global clip offset of this rank (weak scaling)
-    x_all, cond_all = detfill.synthetic_inputs(cfg, B)       # per-rank clips (same synthetic clips per rank)
-    x_host, cond_host = x_all.pin_memory(), cond_all.pin_memory()
+    C, F, S = cfg.data.channels, cfg.data.num_frames, cfg.data.image_size
+    nfp = cfg.sampling.num_frames_pred if args.ar else F           # kept frames per clip and step
+    n_iter = -(-nfp // F) if args.ar else 1                         # sampler calls per step
+    # clips: weak scaling = `batch` clips on every GPU; strong scaling = the workload's batch split over the GPUs
+    if args.scaling == "strong":
+        n_clips = args.batch or cfg.bench_batch
+        lo, hi = runner.shard_range(n_clips, rank, world)
+    else:
+        B_rank = args.batch or cfg.bench_batch
+        n_clips = B_rank * world
+        lo, hi = rank * B_rank, (rank + 1) * B_rank
+    B = hi - lo
+    assert B > 0, f"rank {rank} has no clips ({n_clips} clips over {world} GPUs)"
+    # every clip has its own synthetic data, generated for the GLOBAL clip index (same clip on any GPU count)
+    x_all, cond_all = detfill.synthetic_inputs(cfg, n_clips)
+    x_host, cond_host = x_all[lo:hi].contiguous().pin_memory(), cond_all[lo:hi].contiguous().pin_memory()
     x_dev, cond_dev = x_host.to(dev), cond_host.to(dev)
-    out_host = torch.empty_like(x_host).pin_memory()
+    out_host = torch.empty((n_clips, C * nfp, S, S), dtype=torch.float32).pin_memory() if rank == 0 else None
     kw = dict(final_only=True, denoise=True, subsample_steps=L, clip_before=True, verbose=False, log=False)
 
+    def generate(i, xd, cd):
+        """this rank's clips: one sampler call, or the whole AR loop; frames in [0, 1]"""
+        if args.ar:
+            return runner.video_gen_clips(cfg, net, cd, nfp, clip_offset=lo, philox_seed=1234 + i,
+                                          init_fn=lambda k, shape: xd if k == 0 else torch.randn(shape, device=dev),
+                                          sampler=samplers.ddpm_sampler, sampler_kwargs=dict(subsample_steps=L))
+        gen = samplers.ddpm_sampler(xd, net, cond=cd, philox_seed=1234 + i, clip_offset=lo, **kw)[-1]
+        return runner.inverse_data_transform(cfg, gen)
+
     def step_resident(i):
-        return samplers.ddpm_sampler(x_dev, net, cond=cond_dev, philox_seed=1234 + i, clip_offset=lo, **kw)
+        return generate(i, x_dev, cond_dev)
 
     def step_e2e(i):
         xd = x_host.to(dev, non_blocking=True)
         cd = cond_host.to(dev, non_blocking=True)
-        gen = samplers.ddpm_sampler(xd, net, cond=cd, philox_seed=1234 + i, clip_offset=lo, **kw)[-1]
-        out_host.copy_(gen.reshape(out_host.shape), non_blocking=True)
+        frames = generate(i, xd, cd)
+        allf = runner.gather_clips(frames, n_clips, rank, world)      # the one collective of the path (NCCL all-gather)
+        if rank == 0:
+            out_host.copy_(allf.reshape(out_host.shape), non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return runner.inverse_data_transform(cfg, out_host)
+        return out_host
 
     def barrier():
         if world > 1:
@@ -264,17 +371,17 @@ def main():
         barrier()
         return ms
 
-    log(f"module built; B={B} L={L}; warm-up x{args.warmup}")
+    log(f"module built; clips {lo}..{hi} of {n_clips} (B={B}), L={L}, {n_iter} sampler call(s) per step; warm-up x{args.warmup}")
     for i in range(args.warmup):
         step_resident(i)
         torch.cuda.synchronize()
         log(f"warm-up step {i} done")
-    launches_per_step = samplers.ddpm_sampler.last_launches
+    launches_per_step = samplers.ddpm_sampler.last_launches * n_iter
     clocks = ClockSampler(local)
     clocks.start()
     ms = timed(step_resident, args.steps)
     clk = clocks.stop()
-    frames_per_step = B * F * world
+    frames_per_step = n_clips * nfp
     value = frames_per_step * args.steps / (ms / 1e3)
     log(f"resident: {ms / args.steps:.1f} ms/step -> {value:.1f} frames/s")
     for i in range(min(args.warmup, 1)):
@@ -286,24 +393,31 @@ def main():
     gf = algorithmic_gflop_per_forward(cfg)
     pk, pk_src = peaks()
     P = net.engine().program(B)
+    calls = (L + 1) * n_iter                                        # network evaluations per clip and step
+    gen_frames = n_clips * F * n_iter                               # frames generated (the AR loop keeps nfp of them)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split on tcgen05, fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {describe(cfg)}", "clips_per_gpu": B, "global_clips": B * world,
-                   "parallelism": f"clip-sharded x{world}, no data-path collective",
+        "config": {"workload": f"{args.workload}: {describe(cfg)}", "clips_per_gpu": B, "global_clips": n_clips,
+                   "mode": (f"autoregressive video_gen: {n_iter} sampler calls per step, {nfp} frames kept of "
+                            f"{F * n_iter} generated per clip" if args.ar else "one ddpm_sampler call per step"),
+                   "parallelism": f"clip-sharded x{world} (distinct clips per rank, global clip ids), no data-path "
+                                  f"collective; one NCCL all-gather of the finished frames inside the e2e region",
                    "l2": "working set (weights 4x%.0f MB + GBs of activations per forward) exceeds the 126 MB L2; no flush needed"
                          % (sum(p.numel() for p in net.parameters()) / 1e6),
                    "conv_backend": net.engine().conv_mode, "noise": "in-kernel Philox4x32-10 keyed by global clip id"},
         "e2e": {"value": e2e_val, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (x_host.numel() + cond_host.numel()) * 4 * world,
-                "d2h_bytes_per_step": out_host.numel() * 4 * world},
+                "d2h_bytes_per_step": n_clips * C * nfp * S * S * 4,
+                "allgather_bytes_per_rank_per_step": (B * C * nfp * S * S * 4) if world > 1 else 0},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
+        "frames_generated_per_s": gen_frames * args.steps / (ms / 1e3),
         "flops": {"algorithmic_gflop_per_sample_forward": gf,
-                  "algorithmic_tflop_per_frame": gf * (L + 1) / F / 1e3,
-                  "whole_path_achieved_tflops": value * gf * (L + 1) / F / 1e3 / world,
-                  "whole_path_frac_of_bf16_peak": value * gf * (L + 1) / F / 1e3 / world / pk["bf16_tflops_sustained"],
+                  "algorithmic_tflop_per_kept_frame": gf * calls / nfp / 1e3,
+                  "whole_path_achieved_tflops": value * gf * calls / nfp / 1e3 / world,
+                  "whole_path_frac_of_bf16_peak": value * gf * calls / nfp / 1e3 / world / pk["bf16_tflops_sustained"],
                   "note": "tensor work executed = 3x algorithmic (fp16 hi/lo split for fp32 parity)"},
     }
 
@@ -311,15 +425,16 @@ def main():
         line["roofline"] = roofline(net, P, B, cfg, pk, pk_src)
     if rank == 0 and world == 1 and not args.no_psnr:
         log("PSNR check (CUDA path vs oracle on CPU, 1 clip)")
-        line["psnr_vs_oracle_db"] = psnr_check(cfg, net, sd, dev, steps=args.psnr_steps or L)
-        line["psnr_steps"] = args.psnr_steps or L
+        line["psnr_vs_oracle_db"] = psnr_check(cfg, net, sd, dev, steps=args.psnr_steps or min(L, 100))
+        line["psnr_steps"] = args.psnr_steps or min(L, 100)
         log(f"psnr {line['psnr_vs_oracle_db']:.1f} dB")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        log("CPU baseline (oracle port)")
-        v, dt = cpu_forward_rate(cfg, sd, args.cpu_batch, n_fwd=2)
-        line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                "sample": f"2 timed forwards of the oracle port at batch {args.cpu_batch} "
-                                          f"({dt:.2f} s each), extrapolated x{L + 1} calls"}
+        log("CPU baseline: one full sampler call on the host cores")
+        arm = CpuArm(cfg, args.workload, 1)
+        arm.forward()
+        dt = arm.sample()
+        line["cpu_baseline"] = {"value": cfg.data.num_frames / dt, "unit": "frames/s", "cores": arm.threads,
+                                "kind": arm.kind, "sample": arm.describe(dt)}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -357,7 +472,7 @@ def roofline(net, P, B, cfg, pk, pk_src):
             k = tot.setdefault(op.kind, [0.0, 0])
             k[0] += ms
             k[1] += 2 if op.kind == lib.OP_ATTENTION_UMMA else 1   # pre-split + attention kernels
-            if op.kind == lib.OP_CONV_UMMA and rep == 0:
+            if op.kind in (lib.OP_CONV_UMMA, lib.OP_CONV_UMMA2) and rep == 0:
                 flops_umma += 2.0 * op.B * op.H * op.W * (op.C0 + op.C1) * op.Cout * op.i0 * op.i0
     names = {v: k for k, v in vars(lib).items() if k.startswith("OP_")}
     per_kind = {names[k][3:].lower(): {"ms_per_forward": v[0] / reps, "launches_per_forward": v[1] // reps}
@@ -366,13 +481,14 @@ def roofline(net, P, B, cfg, pk, pk_src):
     out = {"bound": "tensor", "unit": "TFLOP/s", "peak": pk["bf16_tflops_sustained"],
            "peak_source": f"{pk_src} cuBLAS bf16 sustained (MEASURED_PEAKS.json)", "traffic": None,
            "per_kind": per_kind, "forward_ms_sum_of_kernels": total_ms}
-    if lib.OP_CONV_UMMA in tot:
-        n_umma = tot[lib.OP_CONV_UMMA][1] // reps
+    conv_kind = lib.OP_CONV_UMMA if lib.OP_CONV_UMMA in tot else lib.OP_CONV_UMMA2
+    if conv_kind in tot:
+        n_umma = tot[conv_kind][1] // reps
         # algorithmic HBM bytes of the kernel: every conv reads its input(s) and writes its output once (fp32),
         # plus residual and the packed weights
         alg_bytes = 0.0
         for op in P.step_ops:
-            if op.kind == lib.OP_CONV_UMMA:
+            if op.kind == conv_kind:
                 px = op.B * op.H * op.W
                 alg_bytes += 4.0 * px * (op.C0 + op.C1 + op.C2 + op.C3 + op.Cout * (2 if op.aux0 else 1))
                 alg_bytes += 4.0 * op.Cout * ((op.C0 + op.C1) * op.i0 * op.i0 + op.C2 + op.C3)
@@ -384,9 +500,10 @@ def roofline(net, P, B, cfg, pk, pk_src):
                                    f"({tj['launches_per_forward']} launches, {tj['dram_bytes_per_forward'] / 1e9:.2f} GB per "
                                    f"forward); algorithmic {alg_bytes / 1e9:.2f} GB per forward")
         out["algorithmic_bytes_per_launch"] = alg_bytes / max(n_umma, 1)
-        ms_umma = tot[lib.OP_CONV_UMMA][0] / reps
+        ms_umma = tot[conv_kind][0] / reps
         ach = flops_umma / (ms_umma / 1e3) / 1e12
-        out.update(kernel="k_conv_umma (tcgen05 implicit-GEMM conv, all conv launches of one forward)",
+        out.update(kernel=("k_conv_umma" if conv_kind == lib.OP_CONV_UMMA else "k_conv_umma2 (cta_group::2)") +
+                          " (tcgen05 implicit-GEMM conv, all conv launches of one forward)",
                    achieved=ach, frac=ach / pk["bf16_tflops_sustained"], executed_tflops=3 * ach,
                    executed_frac=3 * ach / pk["bf16_tflops_sustained"],
                    kernel_share_of_forward=ms_umma / total_ms,

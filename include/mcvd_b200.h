@@ -97,10 +97,14 @@ enum {
    * both operands, fp32 accumulation in TMEM), with the GroupNorm/FiLM/SiLU transform of the input
    * fused into the shared-memory staging.  Same semantics as MCVD_OP_CONV_SIMT; see
    * mcvd_b200/csrc/conv_umma.cu.  aux1 = norm table of (src0|src1) or NULL; i1 = n tile; i2 = accumulators
-   * per tile (0 = auto); f1 = weight un-scale.  Optional second K-segment (src2|src3 with C2|C3 channels, RAW,
+   * per tile (0 = auto); i3 = operand split for accuracy experiments (0 | 3 = all three products, 1 = drop
+   * hi*lo_w, 2 = drop lo_a*hi, 4 = hi*hi only); f1 = weight un-scale.  Optional second K-segment (src2|src3 with C2|C3 channels, RAW,
    * centre tap only, weights appended per n-tile): the 1x1 shortcut Conv_2(x) of ResnetBlockBigGANpp
    * (layerspp.py:618-619) accumulated into the same TMEM tile as Conv_1, so
-   * dst = f0 * (Conv_1(act(norm(h))) + Conv_2(x) + bias + residual) in ONE kernel. */
+   * dst = f0 * (Conv_1(act(norm(h))) + Conv_2(x) + bias + residual) in ONE kernel.
+   * dst2 = NULL, or the int64 tile statistics of the stored output (format and meaning as in MCVD_OP_CONV_UMMA2:
+   * [tiles][NJ][2][Cout], mcvd_umma2_stats_bytes() bytes) for the GroupNorm that reads dst next;
+   * aux2 = NULL or int64 [grid][16] cycle counters (tools/umma_timing.py). */
   MCVD_OP_CONV_UMMA = 12,
   /* final 3x3 conv with tiny Cout (<= 16) and fused input norm: conv3x3(SiLU(GN(x))) of
    * ncsnpp_more.py:375-379; aux0 = float4 norm table or NULL. */

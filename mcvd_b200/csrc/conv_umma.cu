@@ -21,7 +21,12 @@
 //     [k-chunk of 8 halfs][position][8 halfs = 16 B]      LBO = positions*16 B,  SBO = 128 B.
 // Outputs at padding positions are computed and discarded (2..20 % of the rows).
 //
-// Warp roles (320 threads, one CTA per SM):
+// Round 2 (measurements in profiles/r2_*): a second MMA-issuing warp (one per accumulator: a single thread's
+// instruction stream, ~8 instructions per MMA at ~7 cycles each, was as slow as the tensor core itself), and the
+// GroupNorm partial sums of the stored output accumulated in the epilogue in exact 64-bit fixed point (replaces
+// the k_gn_partial pass; same format and rationale as conv_umma2.cu).
+//
+// Warp roles (one CTA per SM):
 //   warps 0-7  producers: fp32 NHWC global -> normalise/FiLM/SiLU -> fp16 hi/lo -> smem slab
 //              (generic-proxy stores + fence.proxy.async), then the epilogue (TMEM -> regs -> global)
 //   warp  8    weight loader: cp.async.bulk (TMA 1-D) of pre-packed fp16 hi/lo smem images
@@ -41,7 +46,9 @@ constexpr int NPROD = 256;      // producer threads (warps 0-7)
 constexpr int W_LOAD = 8;       // weight-loader warp
 constexpr int W_MMA = 9;        // TMEM owner + MMA issuer warp
 constexpr int W_EPI = 10;       // first of the 4 epilogue warps (10..13 -> TMEM lane quadrants 2,3,0,1)
-constexpr int NTHREADS = 448;
+constexpr int W_MMA2 = 14;      // second MMA issuer (accumulator 1 of two-accumulator tiles)
+constexpr int NTHREADS = 480;
+constexpr float STAT_SCALE = 65536.0f;   // fixed-point scale of the epilogue statistics
 constexpr int MT = 128;         // rows per accumulator (UMMA M)
 constexpr int TAB_NB = 8;       // images whose norm-table rows are staged in smem per K-block
 
@@ -56,6 +63,8 @@ struct UmmaArgs {
   const float* res;
   const float4* tab;     // norm table [B][Cin] (mean, rstd, G, S) or null
   float* dst;
+  unsigned long long* stats;   // optional: [tiles128][NJ][2][Cout] fixed-point sum / sum of squares of the stored output
+  int NJ;                // image slots per 128-position tile (127 / Pimg + 2)
   long long* dbg;        // optional per-CTA cycle counters (tools/umma_timing.py); null in production
   int B, H, W, C0, C1, Cout;
   int ks;                // 1 or 3
@@ -70,6 +79,7 @@ struct UmmaArgs {
   int tiles_n, ntiles;   // n tiles per m tile, total tiles
   int tmem_cols;
   int act_in, act_out;
+  int split;             // operand split (accuracy experiments): bit 0 = lo*hi term, bit 1 = hi*lo term
   int tab_nb;            // images a tile's slab can touch
   float wscale, oscale;
 };
@@ -118,20 +128,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
   float4* tab_s = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [2][TAB_NB][32]
   float* bias_s = reinterpret_cast<float*>(tab_s + 2 * TAB_NB * 32);                    // [NT]
+  unsigned long long* stat_s = reinterpret_cast<unsigned long long*>(bias_s + 256);     // [NJ][2][NT] (when a.stats)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int taps = a.ks * a.ks;
   const int MTOT = MT * a.NACC;
 
   if (tid == 0) {
+    // one tcgen05.commit per MMA-issuing warp (= per accumulator) on the "consumed" barriers
     for (int i = 0; i < 2; ++i) {
-      mbar_init(A_FULL(i), NPROD); mbar_init(A_EMPTY(i), 1);
-      mbar_init(ACC_FULL(i), 1); mbar_init(ACC_EMPTY(i), 128);
+      mbar_init(A_FULL(i), NPROD); mbar_init(A_EMPTY(i), a.NACC);
+      mbar_init(ACC_FULL(i), a.NACC); mbar_init(ACC_EMPTY(i), 128);
     }
-    for (int i = 0; i < a.NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), 1); }
+    for (int i = 0; i < a.NB; ++i) { mbar_init(B_FULL(i), 1); mbar_init(B_EMPTY(i), a.NACC); }
     fence_barrier_init();
   }
   if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (a.stats)
+    for (int i = tid; i < a.NJ * 2 * a.NT; i += NTHREADS) stat_s[i] = 0ull;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -304,9 +318,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       }
     }
     __syncwarp();
-  } else if (warp == W_MMA) {
-    // =========================== MMA issuer ===========================
-    if (elect_one()) {
+  } else if (warp == W_MMA || warp == W_MMA2) {
+    // =========================== MMA issuers ===========================
+    // warp W_MMA feeds accumulator 0, warp W_MMA2 accumulator 1 (idle for one-accumulator tiles); both wait for the
+    // same slab / weight stages and each commits "consumed" for its own MMAs
+    const int my_acc = (warp == W_MMA) ? 0 : 1;
+    if (my_acc < a.NACC && elect_one()) {
       const uint32_t idesc = make_idesc_f16(MT, a.NT);
       const uint32_t a_lbo16 = (uint32_t)a.HP, b_lbo16 = (uint32_t)a.NT;      // LBO in 16-byte units
       const uint64_t a_proto = make_desc(0, a_lbo16 * 16, 128), b_proto = make_desc(0, b_lbo16 * 16, 128);
@@ -319,22 +336,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         const int set = it % a.nsets;
         DBG_T(tm);
         mbar_wait(ACC_EMPTY(set), ((it / a.nsets) & 1) ^ 1);      // epilogue drained this accumulator set
-        DBG_ADD(5, tm, true);
+        DBG_ADD(5, tm, my_acc == 0);
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(set * a.NACC * a.NT);
         uint32_t accum = 0;                    // 0 only for the very first MMA of each accumulator
         for (int kb = 0; kb < a.nKB; ++kb, ++g) {
           const int st = g & 1;
-          DBG_ADD(8, tm, true);
+          DBG_ADD(8, tm, my_acc == 0);
           mbar_wait(A_FULL(st), (g >> 1) & 1);
-          DBG_ADD(6, tm, true);
+          DBG_ADD(6, tm, my_acc == 0);
           tc_fence_after();
           const uint32_t a_hi16 = a0_16 + (uint32_t)st * a_stage16 + (uint32_t)a.halo0;
           const int ntap = (kb < a.nKB0) ? taps : 1;
           for (int tap = 0; tap < ntap; ++tap) {
-            DBG_ADD(8, tm, true);
+            DBG_ADD(8, tm, my_acc == 0);
             mbar_wait(B_FULL(bst), bph);
-            DBG_ADD(7, tm, true);
+            DBG_ADD(7, tm, my_acc == 0);
             tc_fence_after();
             const int shift = (a.ks == 3 && kb < a.nKB0) ? ((tap / 3 - 1) * a.Wp + (tap % 3 - 1)) : 0;
             const uint32_t a_tap16 = a_hi16 + (uint32_t)shift;
@@ -343,16 +360,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
               const uint64_t dbh = desc_add(b_proto, b_tap16 + (uint32_t)s * b_step16);
               const uint64_t dbl = desc_add(dbh, b_lo16);
               const uint32_t a_s16 = a_tap16 + (uint32_t)(2 * s) * a_lbo16;
-#pragma unroll
-              for (int acc = 0; acc < 2; ++acc) {
-                if (acc < a.NACC) {
-                  const uint64_t dah = desc_add(a_proto, a_s16 + (uint32_t)(acc * MT));
-                  const uint64_t dal = desc_add(dah, a_half16);
-                  const uint32_t d = d0 + (uint32_t)(acc * a.NT);
-                  umma_f16(d, dah, dbh, idesc, accum);
-                  umma_f16(d, dal, dbh, idesc, 1u);
-                  umma_f16(d, dah, dbl, idesc, 1u);
-                }
+              {
+                const uint64_t dah = desc_add(a_proto, a_s16 + (uint32_t)(my_acc * MT));
+                const uint64_t dal = desc_add(dah, a_half16);
+                const uint32_t d = d0 + (uint32_t)(my_acc * a.NT);
+                umma_f16(d, dah, dbh, idesc, accum);
+                if (a.split & 1) umma_f16(d, dal, dbh, idesc, 1u);
+                if (a.split & 2) umma_f16(d, dah, dbl, idesc, 1u);
               }
               accum = 1u;
             }
@@ -362,7 +376,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
           umma_commit(A_EMPTY(st));           // slab of this K-block consumed
         }
         umma_commit(ACC_FULL(set));
-        DBG_ADD(8, tm, true);
+        DBG_ADD(8, tm, my_acc == 0);
       }
     }
     __syncwarp();
@@ -392,8 +406,55 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       tc_fence_after();
       const uint32_t trow0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(set * a.NACC * a.NT);
       for (int acc = 0; acc < a.NACC; ++acc) {
-        int bdummy = 0;
-        const int mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bdummy);
+        int myb = 0;
+        const int mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, myb);
+        // statistics: image slot of this row inside its 128-position tile, and the slots present in this warp
+        const long long q_tile = p0 + (long long)acc * MT;
+        const int tile_b0 = (int)min((long long)(a.B - 1), q_tile / a.Pimg);
+        const int myj = mypix >= 0 ? myb - tile_b0 : -1;
+        unsigned jmask = 0;
+        if (a.stats) {
+#pragma unroll 1
+          for (int jj = 0; jj < 4; ++jj)
+            if (__ballot_sync(0xffffffffu, myj == jj)) jmask |= 1u << jj;
+        }
+        // per-(slot, channel) sums of this warp's rows of one column block -> the CTA's shared accumulators
+        auto stat_block = [&](int cb, int lpr, int qc, int rsub, int rpi) {
+#pragma unroll 1
+          for (int jj = 0; jj < 4; ++jj) {
+            if (!(jmask & (1u << jj))) continue;
+            long long s1[4] = {0, 0, 0, 0};
+            unsigned long long s2[4] = {0, 0, 0, 0};
+#pragma unroll 2
+            for (int row = rsub; row < 32; row += rpi) {
+              if (__shfl_sync(0xffffffffu, myj, row) == jj) {
+                const float4 t = pad[row * 8 + (qc ^ (row & 7))];
+                const float f[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int xi = __float2int_rn(f[e] * STAT_SCALE);       // saturates at +-2^31
+                  s1[e] += xi;
+                  s2[e] += (unsigned long long)((long long)xi * (long long)xi);
+                }
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              for (int o = lpr; o <= 16; o <<= 1) {
+                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
+              }
+            }
+            if (lane < lpr) {
+              unsigned long long* sp = stat_s + (size_t)jj * 2 * a.NT + cb + qc * 4;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                atomicAdd(sp + e, (unsigned long long)s1[e]);
+                atomicAdd(sp + a.NT + e, s2[e]);
+              }
+            }
+          }
+        };
         // row slots of this lane in the transposed (coalesced) phase, for 32-wide blocks: 8 lanes per row
         int px8[8];
 #pragma unroll
@@ -438,8 +499,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
                 v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
                 if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
                 *reinterpret_cast<float4*>(dstp + (long long)px8[k] * a.Cout + n0 + cb + q8 * 4) = v;
+                if (a.stats) pad[row * 8 + (q8 ^ (row & 7))] = v;        // re-read by stat_block (same thread)
               }
             }
+            if (a.stats) stat_block(cb, 8, q8, lane >> 3, 4);
           } else {                                          // 16-wide tail: 4 lanes per row, 8 rows per instruction
             const int q = lane & 3, rsub = lane >> 2;
             const float4 bv = *reinterpret_cast<const float4*>(bias_s + cb + q * 4);
@@ -458,10 +521,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
                 v.x *= a.oscale; v.y *= a.oscale; v.z *= a.oscale; v.w *= a.oscale;
                 if (a.act_out) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
                 *reinterpret_cast<float4*>(dstp + off) = v;
+                if (a.stats) pad[row * 8 + (q ^ (row & 7))] = v;
               }
             }
+            if (a.stats) stat_block(cb, 4, q, rsub, 8);
           }
           __syncwarp();
+        }
+        if (a.stats) {
+          // the four warps' sums of this 128-position tile -> global [tile128][NJ][2][Cout]; re-zero for the next tile
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          const long long tile128 = q_tile / MT;
+          unsigned long long* gp = a.stats + (size_t)tile128 * a.NJ * 2 * a.Cout;
+          for (int i = et; i < a.NJ * 2 * a.NT; i += 128) {
+            const int jp = i / a.NT, n = i - jp * a.NT;
+            gp[(size_t)jp * a.Cout + n0 + n] = stat_s[i];
+            stat_s[i] = 0ull;
+          }
+          asm volatile("bar.sync 2, 128;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -523,7 +600,8 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.s2 = (const float*)op.src2; a.s3 = (const float*)op.src3; a.C2 = op.src2 ? op.C2 : 0; a.C3 = op.src3 ? op.C3 : 0;
   a.bias = (const float*)op.bias; a.res = (const float*)op.aux0; a.tab = (const float4*)op.aux1;
   a.dst = (float*)op.dst;
-  a.dbg = (long long*)op.dst2;
+  a.stats = (unsigned long long*)op.dst2;
+  a.dbg = (long long*)op.aux2;
   a.B = op.B; a.H = op.H; a.W = op.W; a.C0 = op.C0; a.C1 = op.C1; a.Cout = op.Cout; a.ks = op.i0;
   a.NT = op.i1;
   a.KB = pick_kb(op.C0, op.C1);
@@ -559,6 +637,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   a.act_in = (op.flags & MCVD_F_ACT_IN) ? 1 : 0;
   a.act_out = (op.flags & MCVD_F_ACT_OUT) ? 1 : 0;
   a.wscale = op.f1; a.oscale = op.f0;
+  a.split = (op.i3 >= 1 && op.i3 <= 3) ? op.i3 : (op.i3 == 4 ? 0 : 3);
   int cols = a.nsets * a.NACC * a.NT, p2 = 32;
   while (p2 < cols) p2 <<= 1;
   MCVD_CHECK(p2 <= 512, "CONV_UMMA: %d TMEM columns", cols);
@@ -568,9 +647,12 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
     MCVD_CHECK(nb <= TAB_NB || !a.tab, "CONV_UMMA: %dx%d images are too small for the fused-norm path", op.H, op.W);
     a.tab_nb = (nb <= TAB_NB) ? nb : 0;
   }
+  a.NJ = (MT - 1) / a.Pimg + 2;
+  MCVD_CHECK(!a.stats || a.Pimg >= 64, "CONV_UMMA: epilogue statistics need images of >= 64 positions");
   const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
   const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
-  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16 + 1024;   // ... + bias
+  const size_t stat_bytes = a.stats ? (size_t)a.NJ * 2 * a.NT * 8 : 0;
+  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16 + 1024 + stat_bytes;   // ... + bias + stats
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);

@@ -108,9 +108,15 @@ class Engine:
             if cc < 100:
                 raise RuntimeError(f"mcvd_b200 kernels are built for sm_100a only (device reports sm_{cc}: "
                                    f"{lib.last_error()})")
-        # 'umma2' (CTA-pair tcgen05 kernel, default) | 'umma' (round-1 single-CTA kernel) | 'simt' (CUDA cores)
-        self.conv_mode = os.environ.get("MCVD_CONV", "umma2").lower()
+        # 'umma' (single-CTA tcgen05 kernel, default) | 'umma2' (CTA-pair cta_group::2 kernel: correct, but slower on
+        # this network's 96-channel layers -- DESIGN.md section 6) | 'simt' (CUDA cores)
+        self.conv_mode = os.environ.get("MCVD_CONV", "umma").lower()
         self.split_mode = int(os.environ.get("MCVD_SPLIT", "3"))            # operand split (accuracy experiments)
+        # GroupNorm partial sums from the conv epilogue instead of a k_gn_partial pass.  Measured on cfg2 (B200): the
+        # integer statistics make the 4-warp epilogue the bottleneck of the 96-channel layers (+1.0 ms of conv time,
+        # +0.5 ms in the finalize kernels) against 0.97 ms saved, so the separate pass stays the default for the
+        # round-1 kernel; the CTA-pair kernel (8 epilogue warps) always uses them.
+        self.epilogue_stats = os.environ.get("MCVD_EPISTATS", "1" if self.conv_mode == "umma2" else "0") == "1"
         self.attn_mode = os.environ.get("MCVD_ATTN", "umma").lower()        # 'umma' | 'simt'
         self.use_graph = os.environ.get("MCVD_GRAPH", "1") != "0"
         self.packed: Dict[str, object] = {}
@@ -388,9 +394,14 @@ class Engine:
                 kw2 = {}
                 if sc is not None:
                     kw2 = dict(src2=sc[0].t0, src3=sc[0].t1, C2=sc[0].c0, C3=sc[0].c1)
+                st = None
+                pimg = (H + 1) * (H + 1) if ks == 3 else H * H
+                if stats and pimg >= 64 and self.epilogue_stats:   # GroupNorm partial sums from the epilogue
+                    st = keep(torch.zeros(lib.umma2_stats_bytes(B, H, H, ks, cout) // 8, device=dev, dtype=torch.int64))
+                    stats_of[dst.data_ptr()] = (st, ks)
                 emit(ops, lib.OP_CONV_UMMA, H=H, W=H, C0=src.c0, C1=src.c1, Cout=cout, i0=ks, i1=nt, i2=nacc,
-                     f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, aux1=tab,
-                     dst=dst, flags=fl, **kw2)
+                     i3=self.split_mode, f0=scale, f1=wscale, src0=src.t0, src1=src.t1, w=wp, bias=bias, aux0=residual, aux1=tab,
+                     dst=dst, dst2=st, flags=fl, **kw2)
                 P.n_umma += 1
                 return dst
             if tab is not None:

@@ -266,7 +266,7 @@ class Interpreter:
             if op.flags & lib.F_ACT_OUT:
                 y = silu(y)
             self.get(op.dst, y.numel()).copy_(y.reshape(-1))
-            if k == lib.OP_CONV_UMMA2 and op.dst2:
+            if k in (lib.OP_CONV_UMMA, lib.OP_CONV_UMMA2) and op.dst2:
                 self._tile_stats(op, y.reshape(B, H, W, op.Cout))
         elif k == lib.OP_CONV_SMALLN:
             x = self.get(op.src0, B * H * W * op.C0).view(B, H, W, op.C0)

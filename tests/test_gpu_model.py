@@ -19,13 +19,17 @@ RTOL, ATOL = 1e-3, 1e-4
 
 
 def gpu_module(name, conv_mode="umma"):
+    """conv_mode: simt | umma (round-1 tcgen05 kernel, GroupNorm partial pass) | umma+stats (same kernel, GroupNorm
+    partial sums from the conv epilogue) | umma2 (CTA-pair cta_group::2 kernel, epilogue statistics)"""
     cfg, net, sd = make_module(name, DEV)
-    net.engine().conv_mode = conv_mode
+    eng = net.engine()
+    eng.conv_mode = conv_mode.split("+")[0]
+    eng.epilogue_stats = conv_mode in ("umma2", "umma+stats")
     return cfg, net, sd
 
 
 @pytest.mark.parametrize("name", ["tiny", "tiny_spade", "tiny_rgb", "cfg1"])
-@pytest.mark.parametrize("conv_mode", ["simt", "umma"])
+@pytest.mark.parametrize("conv_mode", ["simt", "umma", "umma+stats", "umma2"])
 def test_forward_parity(name, conv_mode):
     cfg, net, sd = gpu_module(name, conv_mode)
     B = cfg.bench_batch
@@ -41,7 +45,15 @@ def test_forward_parity(name, conv_mode):
         bad, mx, _ = allclose_report(mine, orc, RTOL, ATOL)
         assert bad == 0, f"{name}/{conv_mode} t={t} vs oracle: max abs err {mx:.3e}"
     P = net.engine().program(B)
-    assert (P.n_umma > 0) == (conv_mode == "umma")
+    assert (P.n_umma > 0) == (conv_mode != "simt")
+    from mcvd_b200 import lib
+    kinds = {o.kind for o in P.step_ops}
+    assert (lib.OP_CONV_UMMA2 in kinds) == (conv_mode == "umma2")
+    if conv_mode in ("umma2", "umma+stats") and cfg.data.image_size >= 32:
+        # the GroupNorm partial pass is gone wherever the producing conv's epilogue can supply the statistics
+        n_partial = sum(o.kind == lib.OP_GN_PARTIAL for o in P.step_ops)
+        n_final = sum(o.kind == lib.OP_GN_FINALIZE for o in P.step_ops)
+        assert n_partial < n_final // 2, (n_partial, n_final)
 
 
 def test_forward_accepts_float_and_per_sample_labels():
@@ -193,3 +205,85 @@ def test_samplers_accept_dataparallel_style_wrapper():
     a = samplers.ddpm_sampler(x.to(DEV), Wrapper(net), **kw)
     b = samplers.ddpm_sampler(x.to(DEV), net, **kw)
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", ["cfg3", "cfg4", "cfg5"])
+def test_big_configs_forward_vs_oracle(name):
+    """BASELINE.json configs[2..4] at FULL size (163 M-parameter SPADE net; ngf 192 with 192-channel heads; the 128-px
+    five-level net): one clip through the CUDA path against the oracle at two timesteps, rtol 1e-3 / atol 1e-4."""
+    torch.set_num_threads(min(torch.get_num_threads(), 16))
+    cfg, net, sd = gpu_module(name)
+    x, cond = detfill.synthetic_inputs(cfg, 1)
+    for t in (37, 800):
+        tt = torch.tensor([t])
+        mine = net(x.to(DEV), tt.to(DEV), cond=cond.to(DEV)).cpu()
+        ref = O.unet_forward(cfg, sd, x, tt, cond)
+        bad, mx, ratio = allclose_report(mine, ref, RTOL, ATOL)
+        assert bad == 0, f"{name} t={t}: {bad} elements out of tolerance, max abs err {mx:.3e} (x{ratio:.2f} of the limit)"
+    P = net.engine().program(1)
+    assert P.n_umma > 0 and P.n_simt <= 60, (P.n_umma, P.n_simt)     # only SPADE's 10-channel mlp_shared convs may be SIMT
+
+
+def test_cfg2_ten_step_sampler_vs_oracle():
+    """BASELINE.json configs[1] at full size: a 10-step DDPM sampler call (+ denoise) on one clip with injected
+    noise against the oracle's sampler: PSNR >= 50 dB on [0,1] frames and max |diff| < 5e-3."""
+    torch.set_num_threads(min(torch.get_num_threads(), 16))
+    cfg, net, sd = gpu_module("cfg2")
+    L = 10
+    x, cond = detfill.synthetic_inputs(cfg, 1, seed=21)
+    zs = step_noise(x.shape, L, tag="c2z")
+    out = samplers.ddpm_sampler(x.to(DEV), net, cond=cond.to(DEV), final_only=True, denoise=True, subsample_steps=L,
+                                clip_before=True, noise_list=[z.to(DEV) for z in zs])[0].cpu()
+    fn = lambda xx, tt, cc: O.unet_forward(cfg, sd, xx, tt, cc)
+    ref = O.ddpm_sample(fn, O.make_schedule(cfg), x.clone(), cond, L, True, True, noise=zs)[0]
+    to01 = lambda a: ((a + 1) / 2).clamp(0, 1)
+    assert O.psnr01(to01(out), to01(ref)) >= 50.0
+    assert max_err(out, ref) < 5e-3
+
+
+def test_ema_style_data_copy_triggers_repack():
+    """reference EMAHelper.ema() (models/ema.py:23-28) writes through param.data.copy_(), which does NOT bump the
+    parameter's version counter; the engine must still notice (value fingerprint) and repack after a forward."""
+    cfg, net, sd = gpu_module("tiny")
+    B = cfg.bench_batch
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    tt = torch.full((B,), 100, dtype=torch.long, device=DEV)
+    a = net(x.to(DEV), tt, cond=cond.to(DEV)).clone()          # packs weights, builds the program
+    sd2 = {k: v.clone() for k, v in net.state_dict().items()}
+    detfill.randomize_state_dict(sd2, seed=77)
+    versions = [p._version for p in net.parameters()]
+    for name_, p in net.named_parameters():
+        p.data.copy_(sd2[name_].to(p.device))                   # exactly what EMAHelper.ema does
+    assert versions == [p._version for p in net.parameters()]   # the hazard: counters did not move
+    b = net(x.to(DEV), tt, cond=cond.to(DEV))
+    ref = O.unet_forward(cfg, {k: v.cpu() for k, v in sd2.items()}, x, tt.cpu(), cond)
+    assert not torch.allclose(a, b)
+    bad, mx, _ = allclose_report(b.cpu(), ref, RTOL, ATOL)
+    assert bad == 0, mx
+
+
+def test_one_frame_at_a_time_ar_loop_vs_oracle():
+    """sampling.one_frame_at_a_time (reference runners/ncsn_runner.py:1500-1501, 1534-1535): one kept frame per AR
+    iteration, the conditioning window slides by one frame.  Checked against the oracle's restatement of the loop."""
+    cfg, net, sd = gpu_module("tiny")
+    cfg.sampling.one_frame_at_a_time = True
+    nfp = 3
+    B, L = cfg.bench_batch, cfg.sampling.subsample
+    C, F, Fc, S = cfg.data.channels, cfg.data.num_frames, cfg.data.num_frames_cond, cfg.data.image_size
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    shape = (B, C * F, S, S)
+    inits = [detfill.normal(f"of_init{i}", shape) for i in range(nfp)]
+    noises = [step_noise(shape, L, tag=f"of{i}_z") for i in range(nfp)]
+    vid = runner.video_gen_clips(cfg, net, cond.to(DEV), nfp, init_fn=lambda i, sh: inits[i].to(DEV),
+                                 noise_fn=lambda i: [z.to(DEV) for z in noises[i]]).cpu()
+    # oracle: the same loop with the oracle sampler
+    fn = lambda xx, tt, cc: O.unet_forward(cfg, sd, xx, tt, cc)
+    sched = O.make_schedule(cfg)
+    c, preds = cond.clone(), []
+    for i in range(nfp):
+        gen = O.ddpm_sample(fn, sched, inits[i].clone(), c, L, True, True, noise=noises[i])[0]
+        preds.append(gen)
+        c = torch.cat([c[:, C:], gen[:, :C]], dim=1)
+    ref = ((torch.cat(preds, 1)[:, :C * nfp] + 1) / 2).clamp(0, 1)
+    assert vid.shape == ref.shape
+    assert O.psnr01(vid, ref) >= 50.0

@@ -117,13 +117,22 @@ def test_conv(case, kind):
         rc = lib.load().mcvd_umma_pack_weights(taps.data_ptr(), ks * ks, Cin, Cout, nt, kb, pk.data_ptr(), k,
                                                torch.cuda.current_stream().cuda_stream)
         assert rc > 0, lib.last_error()
+        from test_gpu_conv2 import expected_stats
+        pimg = (H + 1) * (H + 1) if ks == 3 else H * H
         for nacc in (1, 2):
             out.zero_()
             fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
+            # epilogue GroupNorm statistics (exact integers of the stored output), when the maps are large enough
+            st = torch.full((lib.umma2_stats_bytes(B, H, H, ks, Cout) // 8,), -7, dtype=torch.int64,
+                            device=DEV) if pimg >= 64 else None
             run([mk(lib.OP_CONV_UMMA, B, H=H, W=H, C0=C0, C1=C1, Cout=Cout, i0=ks, i1=nt, i2=nacc, f0=scale,
-                    f1=2.0 ** (-k), src0=x0d, src1=x1d, w=pk, bias=bd, aux0=rd, aux1=td, dst=out, flags=fl)])
+                    f1=2.0 ** (-k), src0=x0d, src1=x1d, w=pk, bias=bd, aux0=rd, aux1=td, dst=out, dst2=st, flags=fl)])
             err = (out.cpu() - ref).abs().max().item()
             assert err < 2e-5 * max(1.0, ref.abs().max().item()), (case, nacc, err)
+            if st is not None:
+                exp = expected_stats(out.cpu(), ks)
+                ntile = -(-(B * pimg) // 128)          # 128-position tiles that hold positions (the array is sized in pairs)
+                assert torch.equal(st.cpu().view(exp.shape)[:ntile], exp[:ntile]), (case, nacc)
         return
     run(ops)
     err = (out.cpu() - ref).abs().max().item()

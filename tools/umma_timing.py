@@ -30,7 +30,7 @@ us = e0.elapsed_time(e1) * 100
 flops = 2.0 * B * H * H * Cin * Cout * ks * ks
 print(f"conv {Cin}->{Cout} k{ks} @{H}x{H} B={B} nt={nt} nacc={nacc} kb={kb}: {us:.1f} us/launch, {flops/us/1e6:.1f} TF/s algorithmic ({3*flops/us/1e6:.0f} executed)")
 dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-arr[0].dst2 = dbg.data_ptr(); lib.run_program(arr, 1, s); torch.cuda.synchronize()
+arr[0].aux2 = dbg.data_ptr(); lib.run_program(arr, 1, s); torch.cuda.synchronize()
 d = dbg.view(148, 16).double()
 d = d[d[:, 0] > 0].mean(0).tolist()
 print(f"  per CTA cycles {d[0]:.0f} | producer t0: wait A_EMPTY {d[1]:.0f} bar {d[2]:.0f} emit {d[3]:.0f} fence+arrive {d[4]:.0f}")
