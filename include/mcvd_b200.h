@@ -115,8 +115,8 @@ enum {
    * S and the per-tile P.V product in TMEM); same fields plus dst2 = device scratch of at least
    * mcvd_attention_scratch_bytes(B, H*W, C0) bytes (16-byte aligned): a first kernel splits q, k, v into
    * fp16 hi/lo operand images there, the attention kernel streams them in with cp.async.bulk (2 launches).
-   * Head dim in {32,48,64,96,128}, H*W a multiple of the key tile (128, or 64 for head dim 128; 64 when
-   * H*W = 64).  See mcvd_b200/csrc/attention_umma.cu. */
+   * Head dim in {32,48,64,96,128,192}, H*W a multiple of the key tile (128; 64 for head dim 128; 32 for head
+   * dim 192; H*W itself when smaller).  See mcvd_b200/csrc/attention_umma.cu. */
   MCVD_OP_ATTENTION_UMMA = 15,
   /* MCVD_OP_CONV_UMMA on CTA pairs (tcgen05.mma.cta_group::2, M = 256 over the two SMs of a TPC; see
    * mcvd_b200/csrc/conv_umma2.cu).  Same semantics and fields, except:

@@ -212,9 +212,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       mbar_wait(S_FULL, j & 1);
       tc_fence_after();
       // this thread's columns of S(j): read once, kept in registers across the max exchange
-      uint32_t rr[64];
+      uint32_t rr[64];                                      // half_cols = 16 (head dim 192), 32 or 64 of them are live
       tmem_ld16(tS + lane_off + col0, rr);
-      tmem_ld16(tS + lane_off + col0 + 16, rr + 16);
+      if (half_cols >= 32) tmem_ld16(tS + lane_off + col0 + 16, rr + 16);
       if (half_cols == 64) {
         tmem_ld16(tS + lane_off + col0 + 32, rr + 32);
         tmem_ld16(tS + lane_off + col0 + 48, rr + 48);
@@ -222,7 +222,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      if (half_cols >= 32) {
+#pragma unroll
+        for (int e = 16; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
+      }
       if (half_cols == 64) {
 #pragma unroll
         for (int e = 32; e < 64; ++e) mx = fmaxf(mx, __uint_as_float(rr[e]));
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) k_attention_umma(const AttnArg
       float sum = 0.f;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        if (g < 4 || half_cols == 64) {
+        if (g * 8 < half_cols) {
           float p[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -344,10 +348,12 @@ int launch_d(const McvdOp& op, cudaStream_t s) {
   AttnArgs a;
   a.qkv = (const float*)op.src0; a.out = (float*)op.dst;
   a.T = op.H * op.W; a.C = op.C0; a.scale = op.f0;
-  a.KT = (D <= 96) ? 128 : 64;
+  // key tile: as large as the operand images allow in 227 KB (Q is resident: 4*D*128 bytes; K, V^T, P scale with KT)
+  a.KT = (D <= 96) ? 128 : (D <= 128 ? 64 : 32);
   if (a.T < a.KT) a.KT = a.T;
-  // the softmax warps read S in 64-column passes
-  MCVD_CHECK(a.KT % 64 == 0 && a.T % a.KT == 0, "ATTENTION_UMMA: %d tokens not tileable (need a multiple of 64)", a.T);
+  // two softmax threads per query row split the key columns of a tile: 16, 32 or 64 columns each
+  MCVD_CHECK((a.KT == 32 || a.KT == 64 || a.KT == 128) && a.T % a.KT == 0,
+             "ATTENTION_UMMA: %d tokens not tileable by the key tile %d", a.T, a.KT);
   a.nkt = a.T / a.KT;
   int cols = a.KT + D, p2 = 32;
   while (p2 < cols) p2 <<= 1;
@@ -391,9 +397,10 @@ int launch_attention_umma(const McvdOp& op, cudaStream_t s) {
     case 64: return launch_d<64>(op, s);
     case 96: return launch_d<96>(op, s);
     case 128: return launch_d<128>(op, s);
+    case 192: return launch_d<192>(op, s);          // cfg4 (bair_big, n_head_channels = 192): key tile 32
     default: break;
   }
-  set_error("ATTENTION_UMMA: head dim %d unsupported (32/48/64/96/128)", op.i1);
+  set_error("ATTENTION_UMMA: head dim %d unsupported (32/48/64/96/128/192)", op.i1);
   return -1;
 }
 

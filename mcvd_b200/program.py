@@ -576,8 +576,8 @@ class Engine:
             att = f32(B, H, H, C)
             d = C // ms.heads
             T = H * H
-            kt = min(T, 128 if d <= 96 else 64)
-            use_tc = self.attn_mode == "umma" and d in (32, 48, 64, 96, 128) and T % kt == 0 and kt % 64 == 0
+            kt = min(T, 128 if d <= 96 else (64 if d <= 128 else 32))
+            use_tc = self.attn_mode == "umma" and d in (32, 48, 64, 96, 128, 192) and T % kt == 0 and kt in (32, 64, 128)
             if use_tc:
                 # q/k/v operand images (fp16 hi/lo); one scratch serves every attention layer (stream order)
                 need = lib.attention_scratch_bytes(B, T, C)

@@ -215,11 +215,11 @@ def test_apply_fir(mode, spade, B, Hin, C0, C1):
 
 
 @pytest.mark.parametrize("B,H,heads,d", [(2, 8, 1, 32), (2, 16, 2, 48), (1, 32, 2, 96), (2, 8, 4, 96), (1, 16, 1, 192),
-                                         (2, 16, 2, 64), (1, 16, 1, 128)])
+                                         (2, 16, 2, 64), (1, 16, 1, 128), (2, 32, 2, 192), (2, 8, 3, 192)])
 @pytest.mark.parametrize("kind", ["simt", "umma"])
 def test_attention(B, H, heads, d, kind):
-    if kind == "umma" and d not in (32, 48, 64, 96, 128):
-        pytest.skip("tensor-core attention supports head dims 32..128")
+    if kind == "umma" and d not in (32, 48, 64, 96, 128, 192):
+        pytest.skip("tensor-core attention supports head dims 32..192")
     C, T = heads * d, H * H
     qkv = rnd(B, T, 3 * C, seed=4)
     scale = float(int(d) ** (-0.5))
