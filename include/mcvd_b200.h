@@ -133,6 +133,14 @@ enum {
    *          (layerspp.py:474-477) without re-reading the activation;
    *   aux2 = NULL or int64 [grid][16] cycle counters (tools/umma_timing.py). */
   MCVD_OP_CONV_UMMA2 = 16,
+  /* per-frame quality metrics of generated clips on the GPU (reference runners/ncsn_runner.py:1581-1600, which
+   * loops over PIL images on the CPU): src0 = pred, src1 = real, both [B, C0*i0, H, W] fp32 in [0,1] (i0 frames of
+   * C0 = 1|3 channels); dst = float64 [B, i0, 2] = (MSE over the frame's C0*H*W values, SSIM).  SSIM as the
+   * reference calls it: skimage structural_similarity(data_range=255, gaussian_weights=True,
+   * use_sample_covariance=False) on the 8-bit grey images PIL makes (x*255 truncated; RGB -> L = (19595 R + 38470 G +
+   * 7471 B + 32768) >> 16), i.e. 11x11 Gaussian (sigma 1.5) moments, mean over the interior cropped by 5 pixels.
+   * MCVD_F_ROUND: round the [0,1] values first (the reference does for (Stochastic)MovingMNIST, :1596-1599). */
+  MCVD_OP_FRAME_METRICS = 17,
   MCVD_OP__COUNT
 };
 
@@ -144,6 +152,7 @@ enum {
 #define MCVD_F_FILM     (1 << 4)   /* GN_FINALIZE: aux0 is the FiLM table                          */
 #define MCVD_F_CLIP     (1 << 5)   /* DIFFUSION_UPDATE: clamp x0 to [-1, 1]                        */
 #define MCVD_F_PHILOX   (1 << 6)   /* DIFFUSION_UPDATE: draw z in-kernel                           */
+#define MCVD_F_ROUND    (1 << 7)   /* FRAME_METRICS: round the images before the grey conversion   */
 
 typedef struct McvdOp {
   int32_t kind;

@@ -33,6 +33,7 @@ static int dispatch(const McvdOp& op, cudaStream_t s) {
     case MCVD_OP_CONV_SMALLN: return launch_conv_smalln(op, s);
     case MCVD_OP_COPY: return launch_copy(op, s);
     case MCVD_OP_ATTENTION_UMMA: return launch_attention_umma(op, s);
+    case MCVD_OP_FRAME_METRICS: return launch_frame_metrics(op, s);
     default: break;
   }
   set_error("unknown op kind %d", op.kind);

@@ -249,13 +249,18 @@ __global__ void __launch_bounds__(128) k_gn_finalize(GnSrc s0, GnSrc s1, float4*
   long long s1lo = 0, s1hi = 0;                      // tile statistics: 64-bit partials summed as 32-bit halves
   unsigned long long s2lo = 0, s2hi = 0;
   bool any_tiles = false;
-  for (int ci = 0; ci < cg; ++ci) {                  // the group may straddle the two tensors of a virtual concat
-    const int c = g * cg + ci;
-    const GnSrc& sr = (c < C0) ? s0 : s1;
-    const int cl = (c < C0) ? c : c - C0;
+  // the group's channels may straddle the two tensors of a virtual concat: per tensor, the (item, channel) pairs
+  // are spread over all 128 threads (items = pixel chunks or 128-position tiles)
+  for (int k = 0; k < 2; ++k) {
+    const GnSrc& sr = k ? s1 : s0;
+    const int base = k ? C0 : 0;                                   // first global channel of this tensor
+    const int c_lo = max(g * cg, base) - base, c_hi = min(g * cg + cg, base + sr.C) - base;
+    const int nc = c_hi - c_lo;
+    if (nc <= 0) continue;
     if (sr.ks == 0) {
       const double2* part = reinterpret_cast<const double2*>(sr.p);
-      for (int chunk = threadIdx.x; chunk < nchunk; chunk += blockDim.x) {
+      for (int i = threadIdx.x; i < nchunk * nc; i += blockDim.x) {
+        const int chunk = i / nc, cl = c_lo + i % nc;
         const double2 v = part[((long long)b * nchunk + chunk) * sr.C + cl];
         ds += v.x;
         dq += v.y;
@@ -265,9 +270,10 @@ __global__ void __launch_bounds__(128) k_gn_finalize(GnSrc s0, GnSrc s1, float4*
       int pimg, nj;
       gn_tile_geometry(sr.ks, H, W, pimg, nj);
       const long long q0 = (long long)b * pimg, q1 = q0 + pimg - 1;
-      const int t_lo = (int)(q0 >> 7), t_hi = (int)(q1 >> 7);
+      const int t_lo = (int)(q0 >> 7), nt = (int)(q1 >> 7) - t_lo + 1;
       const long long* st = reinterpret_cast<const long long*>(sr.p);
-      for (int t = t_lo + threadIdx.x; t <= t_hi; t += blockDim.x) {
+      for (int i = threadIdx.x; i < nt * nc; i += blockDim.x) {
+        const int t = t_lo + i / nc, cl = c_lo + i % nc;
         long long tb0 = ((long long)t << 7) / pimg;
         if (tb0 > B - 1) tb0 = B - 1;
         const int jj = b - (int)tb0;
@@ -655,6 +661,101 @@ int launch_diffusion_update(const McvdOp& op, cudaStream_t s) {
       op.Cout > 0 ? op.Cout : op.C0, op.f0, op.f1, op.f2,
       op.f3, op.f4, op.f5, op.flags, (uint32_t)op.i0, (uint32_t)op.i1, op.i2, op.i3);
   MCVD_CUDA_LAUNCH_CHECK("diffusion_update");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-frame MSE and SSIM of generated clips (see MCVD_OP_FRAME_METRICS in include/mcvd_b200.h).
+// grid (frames, B); one CTA holds the two 8-bit grey images in shared memory and evaluates the 11x11 Gaussian
+// moments of every interior pixel in fp64 (the interior crop of 5 pixels is exactly the filter radius, so the
+// 'reflect' boundary mode of scipy's gaussian_filter never enters the mean).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_frame_metrics(const float* __restrict__ pred, const float* __restrict__ real,
+                                                       double* __restrict__ out, int C, int nf, int H, int W,
+                                                       int round_first) {
+  extern __shared__ float gm_smem[];
+  float* gx = gm_smem;                 // pred, grey 0..255
+  float* gy = gm_smem + H * W;         // real
+  __shared__ double red[2][8];
+  const int f = blockIdx.x, b = blockIdx.y, HW = H * W;
+  const float* p0 = pred + ((long long)b * nf + f) * C * HW;
+  const float* r0 = real + ((long long)b * nf + f) * C * HW;
+  double se = 0.0;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    int pb[3], rb[3];
+    for (int c = 0; c < C; ++c) {
+      float pv = p0[c * HW + i], rv = r0[c * HW + i];
+      const double d = (double)rv - (double)pv;
+      se += d * d;
+      if (round_first) { pv = rintf(pv); rv = rintf(rv); }          // torch.round: half to even
+      pb[c] = (int)(unsigned char)(int)(pv * 255.0f);               // ToPILImage: mul(255).byte()
+      rb[c] = (int)(unsigned char)(int)(rv * 255.0f);
+    }
+    if (C == 1) { gx[i] = (float)pb[0]; gy[i] = (float)rb[0]; }
+    else {
+      gx[i] = (float)((pb[0] * 19595 + pb[1] * 38470 + pb[2] * 7471 + 0x8000) >> 16);   // PIL RGB -> L
+      gy[i] = (float)((rb[0] * 19595 + rb[1] * 38470 + rb[2] * 7471 + 0x8000) >> 16);
+    }
+  }
+  __syncthreads();
+  // 1-D Gaussian, sigma 1.5, radius 5, normalised (scipy.ndimage._gaussian_kernel1d)
+  double g[11];
+  {
+    double sum = 0.0;
+    for (int k = -5; k <= 5; ++k) { g[k + 5] = exp(-0.5 * (double)(k * k) / 2.25); sum += g[k + 5]; }
+    for (int k = 0; k < 11; ++k) g[k] /= sum;
+  }
+  const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+  const int ih = H - 10, iw = W - 10;
+  double ssum = 0.0;
+  for (int i = threadIdx.x; i < ih * iw; i += blockDim.x) {
+    const int y = i / iw + 5, x = i % iw + 5;
+    double ux = 0, uy = 0, uxx = 0, uyy = 0, uxy = 0;
+    for (int dy = -5; dy <= 5; ++dy) {
+      double rx = 0, ry = 0, rxx = 0, ryy = 0, rxy = 0;
+      const float* px = gx + (y + dy) * W + x, *py = gy + (y + dy) * W + x;
+#pragma unroll
+      for (int dx = -5; dx <= 5; ++dx) {
+        const double a = px[dx], c = py[dx], w = g[dx + 5];
+        rx += w * a; ry += w * c; rxx += w * a * a; ryy += w * c * c; rxy += w * a * c;
+      }
+      const double w = g[dy + 5];
+      ux += w * rx; uy += w * ry; uxx += w * rxx; uyy += w * ryy; uxy += w * rxy;
+    }
+    const double vx = uxx - ux * ux, vy = uyy - uy * uy, vxy = uxy - ux * uy;
+    ssum += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = se; red[1][warp] = ssum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+    out[((long long)b * nf + f) * 2 + 0] = a / ((double)C * HW);
+    out[((long long)b * nf + f) * 2 + 1] = (ih > 0 && iw > 0) ? c / ((double)ih * iw) : 0.0;
+  }
+}
+
+int launch_frame_metrics(const McvdOp& op, cudaStream_t s) {
+  MCVD_CHECK(op.src0 && op.src1 && op.dst, "FRAME_METRICS: null pointer");
+  MCVD_CHECK(op.C0 == 1 || op.C0 == 3, "FRAME_METRICS: %d channels per frame (1 or 3)", op.C0);
+  MCVD_CHECK(op.i0 >= 1 && op.H >= 11 && op.W >= 11, "FRAME_METRICS: %d frames of %dx%d (SSIM needs >= 11x11)", op.i0, op.H, op.W);
+  MCVD_CHECK(op.B <= 65535, "FRAME_METRICS: batch %d too large for the grid", op.B);
+  const size_t smem = (size_t)2 * op.H * op.W * sizeof(float);
+  MCVD_CHECK(smem <= 200 * 1024, "FRAME_METRICS: %dx%d frames do not fit shared memory", op.H, op.W);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_frame_metrics, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    MCVD_CHECK(e == cudaSuccess, "FRAME_METRICS: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  }
+  dim3 grid(op.i0, op.B);
+  k_frame_metrics<<<grid, 256, smem, s>>>((const float*)op.src0, (const float*)op.src1, (double*)op.dst, op.C0, op.i0,
+                                          op.H, op.W, (op.flags & MCVD_F_ROUND) ? 1 : 0);
+  MCVD_CUDA_LAUNCH_CHECK("frame_metrics");
   return 0;
 }
 

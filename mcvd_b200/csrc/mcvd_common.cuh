@@ -49,5 +49,6 @@ int launch_conv_umma2(const McvdOp& op, cudaStream_t s);
 int launch_conv_smalln(const McvdOp& op, cudaStream_t s);
 int launch_copy(const McvdOp& op, cudaStream_t s);
 int launch_attention_umma(const McvdOp& op, cudaStream_t s);
+int launch_frame_metrics(const McvdOp& op, cudaStream_t s);
 
 }  // namespace mcvd

@@ -28,6 +28,7 @@ OP_CONV_SMALLN = 13
 OP_COPY = 14
 OP_ATTENTION_UMMA = 15
 OP_CONV_UMMA2 = 16
+OP_FRAME_METRICS = 17
 
 F_ACT_IN = 1 << 0
 F_ACT_OUT = 1 << 1
@@ -36,6 +37,7 @@ F_DOWN = 1 << 3
 F_FILM = 1 << 4
 F_CLIP = 1 << 5
 F_PHILOX = 1 << 6
+F_ROUND = 1 << 7
 
 ABI_VERSION = 4
 

@@ -121,6 +121,12 @@ class Engine:
         self.use_graph = os.environ.get("MCVD_GRAPH", "1") != "0"
         self.packed: Dict[str, object] = {}
         self.packed_version = None
+        # optional on-disk cache of the packed (kernel-layout fp16 hi/lo) conv weights, keyed by a fingerprint of the
+        # checkpoint: MCVD_WEIGHT_CACHE=<dir>.  Packing a 163 M-parameter checkpoint takes
+        # ~0.3 s of GPU time plus one program build; the cache turns it into a file read.
+        self.cache_dir = os.environ.get("MCVD_WEIGHT_CACHE") or None
+        self.packs_computed = 0
+        self.packs_loaded = 0
         self.programs: Dict[int, Program] = {}
         self.launches_last_forward = 0
 
@@ -147,6 +153,44 @@ class Engine:
     def _sd(self, key):
         return self._params[key]
 
+    # -- packed-weight disk cache -----------------------------------------------------------------------
+    def _cache_path(self):
+        if not self.cache_dir or self.backend is not None or self.packed_version is None:
+            return None
+        import hashlib
+        ids, fp = self.packed_version
+        h = hashlib.sha256()
+        h.update(repr((lib.ABI_VERSION, self.conv_mode, self.split_mode, [sh for _, sh in ids])).encode())
+        h.update(fp.detach().cpu().numpy().tobytes())
+        return os.path.join(self.cache_dir, f"mcvd_b200_packed_{h.hexdigest()[:32]}.pt")
+
+    def _load_weight_cache(self):
+        path = self._cache_path()
+        if path is None or not os.path.exists(path):
+            return
+        try:
+            blob = torch.load(path, map_location=self.device)
+        except Exception:
+            return                                       # unreadable cache: pack again
+        for k, (t, scale) in blob.items():
+            self.packed[k] = (t.to(self.device), scale)
+            self._cache_loaded_keys.add(k)
+        self.packs_loaded += len(blob)
+
+    def _save_weight_cache(self):
+        path = self._cache_path()
+        if path is None:
+            return
+        blob = {k: (v[0].cpu(), v[1]) for k, v in self.packed.items()
+                if isinstance(k, tuple) and len(k) > 1 and k[1] in ("umma", "umma2")}
+        if not blob or set(blob) <= self._cache_loaded_keys:
+            return                                       # nothing new since the cache was read
+        os.makedirs(self.cache_dir, exist_ok=True)
+        tmp = f"{path}.tmp{os.getpid()}"
+        torch.save(blob, tmp)
+        os.replace(tmp, path)
+        self._cache_loaded_keys = set(blob)
+
     def ensure_packed(self):
         v = self._version()
         if self.packed_version is not None and self.packed_version[0] == v[0] and \
@@ -156,6 +200,8 @@ class Engine:
         self.packed = {}
         self.programs = {}          # programs hold pointers into the packed tensors
         self.packed_version = v
+        self._cache_loaded_keys = set()
+        self._load_weight_cache()
         ns = self.spec
         # timestep-embedding frequencies, exactly as the reference computes them (layers.py:508-511)
         half = ns.nf // 2
@@ -192,6 +238,7 @@ class Engine:
     def _pack_umma(self, taps: torch.Tensor, nt: int, kb: int):
         if self.backend is not None:
             return self.backend.pack_umma(taps, nt, kb)
+        self.packs_computed += 1
         T, I, O = taps.shape
         amax = float(taps.abs().max().item())
         k = 0 if amax == 0.0 else int(math.floor(math.log2(512.0 / amax)))
@@ -210,6 +257,7 @@ class Engine:
             both = torch.cat([taps.reshape(-1), taps_sc.reshape(-1)]).contiguous()
             t, _ = self.backend.pack_umma(both, nt, kb)
             return t, 1.0
+        self.packs_computed += 1
         amax = float(max(taps.abs().max().item(), taps_sc.abs().max().item()))
         k = 0 if amax == 0.0 else int(math.floor(math.log2(512.0 / amax)))
         k = max(-24, min(24, k))
@@ -231,6 +279,7 @@ class Engine:
             flat = taps.reshape(-1) if taps_sc is None else torch.cat([taps.reshape(-1), taps_sc.reshape(-1)])
             t, _ = self.backend.pack_umma(flat.contiguous(), nt, kb)
             return t, 1.0
+        self.packs_computed += 1
         amax = float(taps.abs().max().item())
         if taps_sc is not None:
             amax = max(amax, float(taps_sc.abs().max().item()))
@@ -269,6 +318,7 @@ class Engine:
                 torch.cuda.empty_cache()
         with self._devctx():
             self.programs[B] = self._build(B)
+            self._save_weight_cache()
         if self.backend is not None:
             self._register_all(self.programs[B])
         return self.programs[B]

@@ -170,3 +170,62 @@ def video_gen_sharded(config, scorenet, cond_all: torch.Tensor, rank: int, world
 
     local = video_gen_clips(config, scorenet, cond, init_fn=init_fn, clip_offset=lo, philox_seed=philox_seed, **kw)
     return gather_clips(local, n, rank, world)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# evaluation of generated clips on the GPU
+# ---------------------------------------------------------------------------------------------------------------
+def frame_metrics(config, pred: torch.Tensor, real: torch.Tensor) -> torch.Tensor:
+    """Per-frame MSE and SSIM of generated clips, on the GPU: float64 [B, frames, 2].
+
+    Replaces the reference's per-frame CPU loop over PIL images (runners/ncsn_runner.py:1581-1600).  ``pred`` and
+    ``real`` are [B, C*frames, S, S] in [0, 1] (``inverse_data_transform`` output).  MovingMNIST-style datasets get the
+    reference's rounding before the grey conversion (:1596-1599)."""
+    from . import lib
+    C, S = config.data.channels, config.data.image_size
+    B, CF = pred.shape[0], pred.shape[1]
+    dev = pred.device
+    if dev.type != "cuda":
+        raise RuntimeError("mcvd_b200.runner.frame_metrics runs on CUDA tensors only (no CPU fallback)")
+    p = pred.contiguous().float()
+    r = real.to(dev).contiguous().float()
+    out = torch.empty(B, CF // C, 2, dtype=torch.float64, device=dev)
+    op = lib.McvdOp()
+    op.kind, op.B, op.H, op.W, op.C0, op.i0 = lib.OP_FRAME_METRICS, B, S, S, C, CF // C
+    name = str(getattr(config.data, "dataset", "")).upper()
+    op.flags = lib.F_ROUND if name in ("STOCHASTICMOVINGMNIST", "MOVINGMNIST") else 0
+    op.src0, op.src1, op.dst = p.data_ptr(), r.data_ptr(), out.data_ptr()
+    with torch.cuda.device(dev):
+        lib.run_program(lib.make_ops([op]), 1, torch.cuda.current_stream(dev).cuda_stream)
+    return out
+
+
+def best_of_repeats(per_frame: torch.Tensor, preds_per_test: int):
+    """(mse, psnr, ssim) per test clip: video metric = mean over frames, then the best of the clip's
+    ``preds_per_test`` samples (reference runners/ncsn_runner.py:1602-1604, 2194-2196)."""
+    vid_mse = per_frame[..., 0].mean(1)
+    vid_ssim = per_frame[..., 1].mean(1)
+    mse = vid_mse.reshape(-1, preds_per_test).min(-1).values
+    psnr = (10 * torch.log10(1 / vid_mse)).reshape(-1, preds_per_test).max(-1).values
+    ssim = vid_ssim.reshape(-1, preds_per_test).max(-1).values
+    return mse, psnr, ssim
+
+
+@torch.no_grad()
+def evaluate_clips(config, scorenet, X: torch.Tensor, preds_per_test: Optional[int] = None,
+                   num_frames_pred: Optional[int] = None, **gen_kw):
+    """One test batch of the reference's ``video_gen`` (runners/ncsn_runner.py:1392-1395, 1463-1470, 1501-1609): every
+    test clip is repeated ``preds_per_test`` times (``repeat_interleave``, the reference's collate function), each
+    repeat is sampled with its own noise, and the per-clip metrics keep the best repeat.  ``X`` is [B, T, C, S, S] in
+    [0, 1].  Returns (frames [B*p, C*nfp, S, S] in [0, 1], dict of per-clip mse / psnr / ssim tensors)."""
+    p = preds_per_test if preds_per_test is not None else getattr(config.sampling, "preds_per_test", 1)
+    nfp = num_frames_pred if num_frames_pred is not None else config.sampling.num_frames_pred
+    X = X.repeat_interleave(p, dim=0)
+    real, cond, _ = conditioning_fn(config, data_transform(config, X), num_frames_pred=nfp,
+                                    prob_mask_cond=getattr(config.data, "prob_mask_cond", 0.0))
+    dev = next(scorenet.parameters()).device
+    frames = video_gen_clips(config, scorenet, cond.to(dev), nfp, **gen_kw)
+    real01 = inverse_data_transform(config, real.to(dev))
+    per_frame = frame_metrics(config, frames, real01)
+    mse, psnr, ssim = best_of_repeats(per_frame, p)
+    return frames, {"mse": mse, "psnr": psnr, "ssim": ssim, "per_frame": per_frame}

@@ -11,7 +11,7 @@ legs may import this module.  The product package ``mcvd_b200`` never does.
 
 Pinning: the reference has NO tests or golden vectors for this path, so the
 oracle is pinned against the reference *itself*, imported in place on the build container:
-``tests/test_oracle_vs_reference.py`` (runs where /root/reference exists) and the committed
+``tests/test_host_cpu.py::test_oracle_and_module_pinned_to_live_reference`` (runs where /root/reference exists) and the committed
 fixtures in ``tests/golden/`` produced by ``oracle/gen_golden.py`` from the unmodified reference.
 
 Every function cites the reference file:line it restates (paths relative to the reference root).

@@ -287,3 +287,93 @@ def test_one_frame_at_a_time_ar_loop_vs_oracle():
     ref = ((torch.cat(preds, 1)[:, :C * nfp] + 1) / 2).clamp(0, 1)
     assert vid.shape == ref.shape
     assert O.psnr01(vid, ref) >= 50.0
+
+
+def test_packed_weight_disk_cache(tmp_path, monkeypatch):
+    """MCVD_WEIGHT_CACHE: the kernel-layout weight images are written once per checkpoint and read back by the next
+    engine with the same parameter values; another checkpoint gets its own file."""
+    monkeypatch.setenv("MCVD_WEIGHT_CACHE", str(tmp_path))
+    cfg, net, sd = make_module("tiny", DEV)
+    B = cfg.bench_batch
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    tt = torch.full((B,), 300, dtype=torch.long, device=DEV)
+    a = net(x.to(DEV), tt, cond=cond.to(DEV))
+    e1 = net.engine()
+    assert e1.packs_computed > 0 and e1.packs_loaded == 0
+    files = list(tmp_path.glob("mcvd_b200_packed_*.pt"))
+    assert len(files) == 1
+    cfg2_, net2, _ = make_module("tiny", DEV)                 # same deterministic weights -> same fingerprint
+    b = net2(x.to(DEV), tt, cond=cond.to(DEV))
+    e2 = net2.engine()
+    assert e2.packs_computed == 0 and e2.packs_loaded == e1.packs_computed
+    assert torch.equal(a, b)
+    sd2 = {k: v.clone() for k, v in net2.state_dict().items()}
+    detfill.randomize_state_dict(sd2, seed=5)
+    net2.load_state_dict(sd2)                                  # other values: a second cache file, freshly packed
+    net2(x.to(DEV), tt, cond=cond.to(DEV))
+    assert len(list(tmp_path.glob("mcvd_b200_packed_*.pt"))) == 2 and net2.engine().packs_computed > 0
+
+
+def test_patch_install_dispatches_to_the_cuda_path(tmp_path, monkeypatch):
+    """mcvd_b200.patch.install() on a CUDA box.  The reference tree is not shipped to the GPU boxes, so a stub with the
+    reference's module layout (``runners.ncsn_runner.get_model``, ``models.{ddpm,ddim,FPNDM}_sampler`` -- the names
+    main.py / load_model_from_ckpt.py bind, reference runners/ncsn_runner.py:180, models/__init__.py:39,103,207)
+    stands in for it; with the real tree the same code path runs (tests/test_host_cpu.py covers the CPU fallback)."""
+    import importlib
+    import sys
+    (tmp_path / "runners").mkdir()
+    (tmp_path / "models").mkdir()
+    (tmp_path / "runners" / "__init__.py").write_text("")
+    (tmp_path / "models" / "__init__.py").write_text(
+        "def ddpm_sampler(x_mod, scorenet, **kw):\n    return 'reference ddpm'\n"
+        "def ddim_sampler(x_mod, scorenet, **kw):\n    return 'reference ddim'\n"
+        "def FPNDM_sampler(x_mod, scorenet, **kw):\n    return 'reference fpndm'\n")
+    (tmp_path / "runners" / "ncsn_runner.py").write_text(
+        "from models import ddpm_sampler, ddim_sampler, FPNDM_sampler\n"
+        "def get_model(config):\n    return 'reference model'\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for m in ("runners", "runners.ncsn_runner", "models"):
+        sys.modules.pop(m, None)
+    try:
+        from mcvd_b200 import patch, model as fast_model
+        from mcvd_b200 import configs
+        patch.install(verbose=False)
+        R = importlib.import_module("runners.ncsn_runner")
+        M = importlib.import_module("models")
+        cfg = configs.workload("tiny")
+        cfg.device = torch.device(DEV)
+        net = R.get_model(cfg)                                   # fast module for a covered config on CUDA
+        assert isinstance(net, fast_model.UNetMore_DDPM) and next(net.parameters()).is_cuda
+        sd = net.state_dict()
+        detfill.randomize_state_dict(sd, 1234)
+        net.load_state_dict(sd)
+        x, cond = detfill.synthetic_inputs(cfg, 2)
+        L = cfg.sampling.subsample
+        out = M.ddpm_sampler(x.to(DEV), net, cond=cond.to(DEV), final_only=True, subsample_steps=L, philox_seed=1,
+                             n_steps_each=0, step_lr=0.0, config=cfg)      # reference-only kwargs are swallowed
+        assert torch.is_tensor(out) and out.shape == (1,) + tuple(x.shape) and out.is_cuda
+        assert R.ddpm_sampler is M.ddpm_sampler                  # names bound by `from models import ...` follow
+        cfg_cpu = configs.workload("tiny")
+        cfg_cpu.device = torch.device("cpu")
+        assert R.get_model(cfg_cpu) == "reference model"         # uncovered (CPU) config: the reference's own model
+        assert M.ddim_sampler(x, "some reference module") == "reference ddim"
+    finally:
+        for m in ("runners", "runners.ncsn_runner", "models"):
+            sys.modules.pop(m, None)
+
+
+def test_data_parallel_replicas_build_their_own_engine():
+    """torch.nn.DataParallel shallow-copies the module per device (reference runners/ncsn_runner.py:1377): a replica
+    must not share the original's engine (device-0 weights, buffers and CUDA graph)."""
+    cfg, net, sd = gpu_module("tiny")
+    B = cfg.bench_batch
+    x, cond = detfill.synthetic_inputs(cfg, B)
+    tt = torch.full((B,), 10, dtype=torch.long, device=DEV)
+    a = net(x.to(DEV), tt, cond=cond.to(DEV))
+    assert net._engine is not None
+    rep = net._replicate_for_data_parallel()
+    assert rep._engine is None
+    if torch.cuda.device_count() >= 2:
+        dp = torch.nn.DataParallel(net, device_ids=[0, 1])
+        out = dp(x.to(DEV), tt, cond=cond.to(DEV))
+        assert torch.allclose(out.cpu(), a.cpu(), rtol=0, atol=0)

@@ -369,3 +369,25 @@ def test_conv_umma_fused_shortcut(case):
                 src0=hd, w=wpk, bias=bd, aux1=td, dst=out, flags=lib.F_ACT_IN, src2=x0d, src3=x1d, C2=Cs0, C3=Cs1)])
         err = (out.cpu() - ref).abs().max().item()
         assert err < 2e-5 * max(1.0, ref.abs().max().item()), (case, nacc, err)
+
+
+@pytest.mark.parametrize("B,C,nf,S,rnd", [(3, 1, 4, 64, True), (2, 3, 2, 64, False), (1, 3, 2, 128, False), (2, 1, 3, 32, False)])
+def test_frame_metrics_vs_oracle(B, C, nf, S, rnd):
+    """MCVD_OP_FRAME_METRICS (per-frame MSE + SSIM of generated clips) against the CPU restatement of the reference's
+    metric loop (oracle/metrics_oracle.py: runners/ncsn_runner.py:1581-1600 + skimage's SSIM algorithm)."""
+    import numpy as np
+    from oracle import metrics_oracle as M
+    g = torch.Generator().manual_seed(B * 100 + S)
+    real = torch.rand(B, C * nf, S, S, generator=g)
+    real = torch.nn.functional.avg_pool2d(real, 5, 1, 2)                       # some spatial structure
+    real = (real - real.min()) / (real.max() - real.min())
+    pred = (real + 0.08 * torch.randn(real.shape, generator=g)).clamp(0, 1)
+    pred[0, :C] = real[0, :C]                                                  # one identical frame: MSE 0, SSIM 1
+    out = torch.zeros(B, nf, 2, dtype=torch.float64, device=DEV)
+    run([mk(lib.OP_FRAME_METRICS, B, H=S, W=S, C0=C, i0=nf, src0=pred.to(DEV), src1=real.to(DEV), dst=out,
+            flags=lib.F_ROUND if rnd else 0)])
+    ref = M.frame_metrics(pred.numpy(), real.numpy(), C, round_first=rnd)
+    got = out.cpu().numpy()
+    assert got[0, 0, 0] == 0.0 and abs(got[0, 0, 1] - 1.0) < 1e-12
+    assert np.abs(got[..., 0] - ref[..., 0]).max() < 1e-12
+    assert np.abs(got[..., 1] - ref[..., 1]).max() < 1e-9

@@ -208,3 +208,36 @@ def test_patch_shim_installs_and_falls_back_on_cpu():
         assert torch.equal(a, b)
     finally:
         R.get_model, M.ddpm_sampler, M.ddim_sampler, M.FPNDM_sampler = orig
+
+
+def test_metrics_oracle_grey_conversion_and_ssim_properties():
+    """oracle/metrics_oracle.py (checker of MCVD_OP_FRAME_METRICS): the 8-bit grey conversion equals what
+    torchvision's ToPILImage + PIL's convert('RGB').convert('L') produce (reference runners/ncsn_runner.py:1590-1599),
+    and the SSIM restatement has the properties of skimage's (1 on identical images, symmetric, < 1 otherwise)."""
+    import numpy as np
+    from oracle import metrics_oracle as M
+    rng = np.random.RandomState(0)
+    for C in (1, 3):
+        fr = rng.rand(C, 32, 32).astype(np.float32)
+        fr[0, 0, :4] = [0.0, 1.0, 0.5, 0.999]
+        try:
+            from PIL import Image
+            u8 = (torch.from_numpy(fr).mul(255).byte()).numpy()            # torchvision ToPILImage for float tensors
+            img = Image.fromarray(u8[0], mode="L") if C == 1 else Image.fromarray(np.transpose(u8, (1, 2, 0)), mode="RGB")
+            want = np.asarray(img.convert("RGB").convert("L"))
+            assert np.array_equal(M.to_grey_u8(fr), want)
+        except ImportError:
+            pass
+        g = M.to_grey_u8(fr)
+        assert g.dtype == np.uint8 and g.shape == (32, 32)
+    a = (rng.rand(40, 40) * 255).astype(np.uint8)
+    b = np.clip(a.astype(np.int32) + rng.randint(-20, 20, a.shape), 0, 255).astype(np.uint8)
+    assert abs(M.ssim_u8(a, a) - 1.0) < 1e-12
+    s_ab, s_ba = M.ssim_u8(a, b), M.ssim_u8(b, a)
+    assert abs(s_ab - s_ba) < 1e-12 and 0.0 < s_ab < 1.0
+    pf = np.zeros((6, 4, 2))
+    pf[..., 0] = rng.rand(6, 4) * 0.01 + 1e-4
+    pf[..., 1] = rng.rand(6, 4)
+    mse, psnr, ssim = M.best_of_repeats(pf, 3)
+    assert mse.shape == (2,) and np.allclose(mse[0], pf[:3, :, 0].mean(1).min())
+    assert np.allclose(psnr[1], (10 * np.log10(1 / pf[3:, :, 0].mean(1))).max()) and np.allclose(ssim[0], pf[:3, :, 1].mean(1).max())
