@@ -390,7 +390,7 @@ k_conv_umma2(const __grid_constant__ C2Args a, const __grid_constant__ CUtensorM
       // by one warp, in order), waits for its own slabs, and both commit every weight stage (B_EMPTY counts 2).  One
       // warp alone was bound by the latency of its own instruction stream (~130 instructions / ~950 cycles per weight
       // stage at ~7 cycles per dependent instruction, 3x the tensor time of the 6 MMAs: ncu source page in
-      // profiles/r2_ncu_conv2_polling.txt).  The whole warp walks the loops (uniform control flow); only tcgen05.mma /
+      // profiles/r2_ncu_conv2_summary.txt).  The whole warp walks the loops (uniform control flow); only tcgen05.mma /
       // tcgen05.commit sit under elect.sync.  Descriptors differ only in their low word (start address field,
       // < 2^14 16-byte units, never carries into the LBO field).  The waits are plain CTA-scope try_waits: an
       // .acquire.cluster wait compiles to TRYWAIT + CCTL.IVALL (an L1 invalidation per stage), and nothing this thread

@@ -40,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // accumulator, the weight loader): try_wait with an explicit suspend-time hint, so the warp is parked by the
 // hardware instead of spinning.  Without the hint try_wait returns almost immediately: 17 polling warps executed
 // 36 M TRYWAIT+BRA pairs in one conv launch and took a third of all issue slots -- away from the single MMA-issuing
-// warp (profiles/r2_ncu_conv2_polling.txt).
+// warp (profiles/r2_ncu_conv2_summary.txt).
 __device__ __forceinline__ void mbar_wait_parked(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
