@@ -164,6 +164,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
     // store (lanes walk positions => conflict-free).
     const int Cin = a.C0 + a.C1;
     const bool has_tab = a.tab != nullptr;
+    // slabs of <= 128 rows (1x1 convolutions on one accumulator) would leave half the producer threads idle:
+    // two threads share a row there, each taking half of the K-block's 8-channel chunks
+    const bool rsplit = a.HP <= NPROD / 2 && chunks >= 2;
+    const int hrow = rsplit ? (tid & (NPROD / 2 - 1)) : tid;
+    const int ch_lo = rsplit ? (tid / (NPROD / 2)) * (chunks / 2) : 0;
+    const int ch_hi = rsplit ? ch_lo + chunks / 2 : chunks;
     auto tile_b0_of = [&](int t) {
       const long long q_first = (long long)(t / a.tiles_n) * MTOT - a.halo0;
       return q_first <= 0 ? 0 : (int)min((long long)(a.B - 1), q_first / a.Pimg);
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       if (pix == -2) return;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        if (ch < chunks) {
+        if (ch >= ch_lo && ch < ch_hi) {
           uint4 hv = make_uint4(0u, 0u, 0u, 0u), lv = hv;
           if (pix >= 0) {
             float v[8] = {raw[2 * ch].x, raw[2 * ch].y, raw[2 * ch].z, raw[2 * ch].w,
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         const float4* sp = reinterpret_cast<const float4*>(src + (long long)pix * cs + cc0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (j < chunks * 2) raw[j] = __ldg(sp + j);
+          if (j >= ch_lo * 2 && j < ch_hi * 2) raw[j] = __ldg(sp + j);
       }
     };
 
@@ -239,11 +245,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       int ppix[3], pb[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        const int h = tid + i * NPROD;
+        const int h = hrow + i * NPROD;
         ppix[i] = -2;                                      // -2: no such slab row, -1: zero padding
         pb[i] = 0;
         if (h < a.HP) { int b = tb0; ppix[i] = decode_pos(a, p0 - a.halo0 + h, b); pb[i] = b - tb0; }
       }
+      // the fused 1x1 shortcut (second segment) multiplies the centre tap only: its K-blocks stage just the
+      // MTOT rows the tile itself covers, one per thread, instead of the whole haloed slab
+      const bool centre = !single && a.nKB > a.nKB0;
+      int cpix = -2;
+      if (centre && tid < MTOT) { int b = tb0; cpix = decode_pos(a, p0 + tid, b); }
       auto src_of = [&](int kb, const float*& src, int& cs, int& cc0) {
         if (kb < a.nKB0) {
           const int c0 = kb * a.KB;
@@ -259,7 +270,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         const int st = g & 1;
         const float* src; int cs, cc0;
         src_of(kb, src, cs, cc0);
-        if (!single) { fetch(cur, ppix[0], src, cs, cc0); fetch(nxt, ppix[1], src, cs, cc0); }
+        const bool seg2 = centre && kb >= a.nKB0;
+        if (seg2) fetch(cur, cpix, src, cs, cc0);
+        else if (!single) { fetch(cur, ppix[0], src, cs, cc0); fetch(nxt, ppix[1], src, cs, cc0); }
         else if (kb + 1 < a.nKB) { const float* s2; int cs2, cc2; src_of(kb + 1, s2, cs2, cc2); fetch(nxt, ppix[0], s2, cs2, cc2); }
         const bool tab_now = has_tab && kb < a.nKB0;                       // this K-block is normalised
         const bool tab_nxt = has_tab && (kb + 1 < a.nKB0 || (kb + 1 == a.nKB && more));
@@ -272,8 +285,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
         uint8_t* hi_base = a_base + (size_t)st * a_stage_bytes;
         uint8_t* lo_base = hi_base + a_half_bytes;
         const float4* tsm = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(tab_s) + (size_t)st * TAB_NB * 96);
-        emit(cur, ppix[0], pb[0], tid, tsm, hi_base, lo_base, tab_now);
-        if (!single) {
+        if (seg2) emit(cur, cpix, 0, a.halo0 + tid, tsm, hi_base, lo_base, false);
+        else emit(cur, ppix[0], pb[0], hrow, tsm, hi_base, lo_base, tab_now);
+        if (!single && !seg2) {
           emit(nxt, ppix[1], pb[1], tid + NPROD, tsm, hi_base, lo_base, tab_now);
           if (a.HP > 2 * NPROD) {                        // 128-wide images: a third slab row for some threads
             fetch(nxt, ppix[2], src, cs, cc0);
