@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libmcvd_b200.so")
-SOURCES = ["api.cu", "elementwise.cu", "conv_simt.cu", "conv_smalln.cu", "attention_simt.cu", "conv_umma.cu", "conv_umma2.cu",
+SOURCES = ["api.cu", "elementwise.cu", "conv_simt.cu", "conv_smalln.cu", "attention_simt.cu", "conv_umma.cu", "conv_umma2.cu", "conv1x1_umma.cu",
            "attention_umma.cu"]
 HEADERS = [os.path.join(CSRC, "mcvd_common.cuh"), os.path.join(CSRC, "umma_ptx.cuh"), os.path.join(os.path.dirname(HERE), "include", "mcvd_b200.h")]
 

@@ -609,6 +609,10 @@ int pick_kb(int C0, int C1) {
 int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.w && op.dst && (op.C1 == 0 || op.src1), "CONV_UMMA: null pointer");
   MCVD_CHECK(op.i0 == 1 || op.i0 == 3, "CONV_UMMA: kernel size %d unsupported", op.i0);
+  {
+    int rc = 0;                                  // plain 1x1 convolutions: input-stationary kernel (conv1x1_umma.cu)
+    if (try_launch_conv1x1(op, s, rc)) return rc;
+  }
   UmmaArgs a;
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.wpk = (const __half*)op.w;
   a.s2 = (const float*)op.src2; a.s3 = (const float*)op.src3; a.C2 = op.src2 ? op.C2 : 0; a.C3 = op.src3 ? op.C3 : 0;

@@ -46,6 +46,7 @@ int launch_resize_nearest(const McvdOp& op, cudaStream_t s);
 int launch_diffusion_update(const McvdOp& op, cudaStream_t s);
 int launch_conv_umma(const McvdOp& op, cudaStream_t s);
 int launch_conv_umma2(const McvdOp& op, cudaStream_t s);
+bool try_launch_conv1x1(const McvdOp& op, cudaStream_t s, int& rc);   // conv1x1_umma.cu; false = not eligible
 int launch_conv_smalln(const McvdOp& op, cudaStream_t s);
 int launch_copy(const McvdOp& op, cudaStream_t s);
 int launch_attention_umma(const McvdOp& op, cudaStream_t s);

@@ -116,6 +116,10 @@ class Engine:
         # integer statistics make the 4-warp epilogue the bottleneck of the 96-channel layers (+1.0 ms of conv time,
         # +0.5 ms in the finalize kernels) against 0.97 ms saved, so the separate pass stays the default for the
         # round-1 kernel; the CTA-pair kernel (8 epilogue warps) always uses them.
+        # 1x1 skip projection (Conv_2): 'auto' runs it on the input-stationary 1x1 kernel (conv1x1_umma.cu) and adds
+        # the result as the residual of Conv_1 when that kernel takes it (<= 320 input channels), else rides along
+        # Conv_1 as a second K-segment; '1' always fuses (round-1 behaviour), '0' never
+        self.fuse_shortcut = os.environ.get("MCVD_FUSE_SC", "auto")
         self.epilogue_stats = os.environ.get("MCVD_EPISTATS", "1" if self.conv_mode == "umma2" else "0") == "1"
         self.attn_mode = os.environ.get("MCVD_ATTN", "umma").lower()        # 'umma' | 'simt'
         self.use_graph = os.environ.get("MCVD_GRAPH", "1") != "0"
@@ -424,7 +428,9 @@ class Engine:
             if shortcut is not None:                       # (Src, wname, bname): 1x1 Conv_2 of the skip branch
                 sc_src, sc_w, sc_b = shortcut
                 kb2 = lib.umma_kblock(sc_src.c0, sc_src.c1) if kb else 0
-                if kb and nt and kb2 and (tab is None or H >= 8):
+                k1_ok = kb2 == 32 and sc_src.C <= 320 and lib.conv1x1_enabled()
+                fuse = self.fuse_shortcut == "1" or (self.fuse_shortcut == "auto" and not k1_ok)
+                if kb and nt and kb2 and (tab is None or H >= 8) and fuse:
                     kb = min(kb, kb2)
                     sc = (sc_src, self._conv_taps(sd(sc_w)))
                     bias = keep((bias + sd(sc_b).float()).contiguous())

@@ -391,3 +391,60 @@ def test_frame_metrics_vs_oracle(B, C, nf, S, rnd):
     assert got[0, 0, 0] == 0.0 and abs(got[0, 0, 1] - 1.0) < 1e-12
     assert np.abs(got[..., 0] - ref[..., 0]).max() < 1e-12
     assert np.abs(got[..., 1] - ref[..., 1]).max() < 1e-9
+
+
+K1_CASES = [
+    # B, H, C0, C1, Cout, tab, act_in, res, act_out      -- the input-stationary 1x1 kernel (conv1x1_umma.cu)
+    (2, 16, 64, 0, 192, True, False, False, False),
+    (2, 8, 96, 0, 96, False, False, True, False),
+    (3, 8, 96, 96, 96, False, False, False, False),        # concatenated sources, 192 rows: a partial last tile
+    (2, 16, 192, 0, 576, True, False, False, False),       # q/k/v projection: 3 n tiles spread over CTA groups
+    (1, 8, 288, 0, 864, True, True, False, False),         # n tile 144 (16-wide tail block), 9 K-blocks, half a tile
+    (2, 32, 96, 96, 96, False, False, True, True),
+    (5, 32, 192, 0, 192, False, False, True, False),
+    (40, 16, 192, 0, 576, True, False, False, False),      # 80 m tiles x 3 n tiles per CTA
+    (8, 64, 96, 96, 96, False, False, False, False),       # 256 m tiles: several work items per CTA (phase wrap)
+    (6, 64, 96, 0, 288, True, False, True, False),
+    (2, 8, 384, 0, 96, False, False, False, False),        # 12 K-blocks: not resident -> general kernel
+]
+
+
+@pytest.mark.parametrize("case", K1_CASES)
+def test_conv1x1_stationary(case):
+    """1x1 convolutions through OP_CONV_UMMA: the input-stationary kernel against the fp64 reference, and bit-exact
+    against the general kernel (forced by asking for epilogue statistics, which the stationary kernel declines)."""
+    B, H, C0, C1, Cout, use_tab, act_in, use_res, act_out = case
+    Cin = C0 + C1
+    x0 = rnd(B, H, H, C0, seed=11)
+    x1 = rnd(B, H, H, C1, seed=12) if C1 else None
+    w = rnd(Cout, Cin, 1, 1, seed=15) / math.sqrt(Cin)
+    bias = rnd(Cout, seed=16) * 0.1
+    res = rnd(B, H, H, Cout, seed=17) if use_res else None
+    tab = make_table(B, Cin) if use_tab else None
+    scale = 0.7071
+    xin = x0 if x1 is None else torch.cat([x0, x1], 3)
+    xa = ref_norm(xin, tab, act_in) if use_tab else xin
+    ref = conv_ref(xa, w, bias, res, scale, act_out)
+    d = lambda t: None if t is None else t.to(DEV).contiguous()
+    x0d, x1d, bd, rd, td = d(x0), d(x1), d(bias), d(res), d(tab)
+    taps = taps_of(w).to(DEV)
+    kb = lib.umma_kblock(C0, C1)
+    nt = max(dd for dd in range(16, 257, 16) if Cout % dd == 0)
+    pk = torch.empty(taps.numel() * 4, dtype=torch.uint8, device=DEV)
+    k = int(math.floor(math.log2(512.0 / float(taps.abs().max()))))
+    rc = lib.load().mcvd_umma_pack_weights(taps.data_ptr(), 1, Cin, Cout, nt, kb, pk.data_ptr(), k,
+                                           torch.cuda.current_stream().cuda_stream)
+    assert rc > 0, lib.last_error()
+    fl = (lib.F_ACT_IN if act_in else 0) | (lib.F_ACT_OUT if act_out else 0)
+    outs = []
+    for general in (False, True):
+        out = torch.full((B, H, H, Cout), float("nan"), device=DEV)
+        st = torch.zeros(lib.umma2_stats_bytes(B, H, H, 1, Cout) // 8, dtype=torch.int64, device=DEV) \
+            if general and H * H >= 64 else None
+        run([mk(lib.OP_CONV_UMMA, B, H=H, W=H, C0=C0, C1=C1, Cout=Cout, i0=1, i1=nt, i2=0, f0=scale, f1=2.0 ** (-k),
+                src0=x0d, src1=x1d, w=pk, bias=bd, aux0=rd, aux1=td, dst=out, dst2=st, flags=fl)])
+        o = out.cpu()
+        err = (o - ref).abs().max().item()
+        assert err < 2e-5 * max(1.0, ref.abs().max().item()), (case, general, err)
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1]), case

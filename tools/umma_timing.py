@@ -33,5 +33,12 @@ dbg = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 arr[0].aux2 = dbg.data_ptr(); lib.run_program(arr, 1, s); torch.cuda.synchronize()
 d = dbg.view(148, 16).double()
 d = d[d[:, 0] > 0].mean(0).tolist()
+if ks == 1 and os.environ.get("MCVD_CONV1X1", "1") != "0" and Cin % 32 == 0 and Cin <= 320:   # conv1x1_umma.cu slots
+    e0.record(); [lib.run_program(arr, 1, s) for _ in range(5)]; e1.record(); torch.cuda.synchronize()
+    print(f"  [stationary kernel, DBG build: {e0.elapsed_time(e1) * 200:.1f} us/launch, dbgf={os.environ.get('MCVD_K1_DBGF', '0')}]")
+    print(f"  per CTA cycles {d[0]:.0f} | producer t0: wait RAW_FULL {d[1]:.0f} work {d[2]:.0f} | loader: wait B_EMPTY {d[11]:.0f}")
+    print(f"  MMA: wait ACC_EMPTY {d[3]:.0f} A_FULL {d[4]:.0f} B_FULL {d[5]:.0f} issue {d[6]:.0f} | epilogue w0: wait ACC_FULL {d[7]:.0f} "
+          f"tmem {d[8]:.0f} transpose {d[9]:.0f} store {d[10]:.0f}")
+    sys.exit(0)
 print(f"  per CTA cycles {d[0]:.0f} | producer t0: wait A_EMPTY {d[1]:.0f} bar {d[2]:.0f} emit {d[3]:.0f} fence+arrive {d[4]:.0f}")
 print(f"  MMA: wait ACC_EMPTY {d[5]:.0f} A_FULL {d[6]:.0f} B_FULL {d[7]:.0f} issue {d[8]:.0f} | epilogue w10: wait ACC_FULL {d[9]:.0f} drain {d[10]:.0f}")
