@@ -52,7 +52,8 @@ constexpr int K1_W_ALOAD = K1_W_EPI + K1_EPI_WARPS;   // input loader (TMA)
 constexpr int K1_THREADS = (K1_W_ALOAD + 1) * 32;
 constexpr int K1_MT = 128;
 constexpr int K1_KB = 32;
-constexpr int K1_MAX_KB = 10;
+constexpr int K1_MAX_KB = 24;      // <= 768 input channels
+constexpr int K1_RING = 8;         // operand stages when the tile is not resident
 constexpr int K1_TAB_IMGS = 3;     // images a 128-position tile can touch (images of >= 64 positions)
 constexpr uint32_t K1_A_STAGE = 2u * 4u * K1_MT * 16u;     // hi | lo, 4 chunks of 8 channels, 16 B per row
 
@@ -63,17 +64,6 @@ __device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* tm
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(row0)
       : "memory");
-}
-
-// 256-bit global accesses (sm_100: LDG.256 / STG.256); 32-byte aligned addresses
-__device__ __forceinline__ void ldg256(const float* p, float v[8]) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg256(float* p, const float v[8]) {
-  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-               "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]));
 }
 
 struct K1Args {
@@ -88,6 +78,7 @@ struct K1Args {
   long long Qtot;          // positions (B * H * W)
   int Pimg, B, Cout;
   int NT, tiles_n, nKB, NB, nsets, tmem_cols;
+  int NA;                  // operand stages: == nKB (tile resident, n-tiles loop over it) or a ring of fewer (one n-tile per item)
   int n_items, n_groups, npg;   // work items = m-tiles x n-groups; n-tiles per group
   int act_in, act_out, split;
   float wscale, oscale;
@@ -111,12 +102,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
   const uint32_t b_stage_bytes = 2u * b_step_bytes;
   const int Cin = a.C0 + a.C1;
   uint8_t* a_base = smem_raw;
-  uint8_t* b_base = a_base + (size_t)a.nKB * K1_A_STAGE;
+  uint8_t* b_base = a_base + (size_t)a.NA * K1_A_STAGE;
   float* bias_s = reinterpret_cast<float*>(b_base + (size_t)a.NB * b_stage_bytes);                 // [Cout]
   float* tab_s = bias_s + a.Cout;                            // [2 items][K1_TAB_IMGS][mean | rstd*G | S][Cin] (when a.tab)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab_s + (a.tab ? 2 * K1_TAB_IMGS * 3 * Cin : 0));
   const uint32_t bar0 = smem_u32(bars);
-  const int NA = a.nKB;
+  const int NA = a.NA;
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };
   auto A_EMPTY = [&](int i) { return bar0 + 8u * (NA + i); };
   auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * NA + i); };
@@ -146,7 +137,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
     // =========================== producers ===========================
     const int grp = tid / K1_GROUP, r = tid % K1_GROUP;
     const bool use_tab = a.tab != nullptr && !(DBG && (a.dbgf & 4));
-    int it = 0;
+    int it = 0, g = 0;                                          // g: K-blocks staged so far (all items)
     unsigned d1 = 0, d2 = 0;
     K1_T0(tp);
     for (int w = blockIdx.x; w < a.n_items; w += gridDim.x, ++it) {
@@ -167,11 +158,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
         }
         named_bar_sync(1, 2 * K1_GROUP);
       }
-      for (int kb = grp; kb < a.nKB; kb += 2) {
+      for (int kb = 0; kb < a.nKB; ++kb, ++g) {
+        const int st = g % NA;
+        // even stages belong to group 0, odd ones to group 1: a stage's barriers are then only ever waited on by one
+        // group, in order (a group that could run a whole phase ahead of another's stage would alias the parity bit)
+        if ((st & 1) != grp) continue;
         K1_ACC(d2, tp);
-        mbar_wait(RAW_FULL(kb), it & 1);                      // the raw fp32 box of this K-block has landed in the stage
+        mbar_wait(RAW_FULL(st), (g / NA) & 1);                // the raw fp32 box of this K-block has landed in the stage
         K1_ACC(d1, tp);
-        uint8_t* hi_base = a_base + (size_t)kb * K1_A_STAGE;
+        uint8_t* hi_base = a_base + (size_t)st * K1_A_STAGE;
         uint8_t* lo_base = hi_base + K1_A_STAGE / 2;
         float4 cur[8];
         {
@@ -210,7 +205,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
         }
         fence_proxy_async();          // generic-proxy stores -> visible to the tensor-core proxy
         __syncwarp();
-        if (lane == 0) mbar_arrive(A_FULL(kb));
+        if (lane == 0) mbar_arrive(A_FULL(st));
       }
     }
     if (DBG && tid == 0) { dbg[1] = d1; dbg[2] = d2; }
@@ -263,12 +258,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
           uint32_t accum = 0;
           for (int kb = 0; kb < a.nKB; ++kb) {
             K1_ACC(d6, tm);
-            if (n == n_lo) { mbar_wait(A_FULL(kb), it & 1); }
+            const int g = it * a.nKB + kb, st = g % NA;
+            if (n == n_lo) { mbar_wait(A_FULL(st), (g / NA) & 1); }
             K1_ACC(d4, tm);
             mbar_wait(B_FULL(bst), bph);
             K1_ACC(d5, tm);
             tc_fence_after();
-            const uint32_t a_st16 = a0_16 + (uint32_t)kb * (K1_A_STAGE >> 4);
+            const uint32_t a_st16 = a0_16 + (uint32_t)st * (K1_A_STAGE >> 4);
             const uint32_t b_st16 = b0_16 + (uint32_t)bst * b_stage16;
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
@@ -283,7 +279,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
             }
             umma_commit(B_EMPTY(bst));
             if (++bst == a.NB) { bst = 0; bph ^= 1; }
-            if (n == n_hi - 1) umma_commit(A_EMPTY(kb));       // the resident tile's K-block may be overwritten
+            if (n == n_hi - 1) umma_commit(A_EMPTY(st));       // this K-block's stage may be overwritten
           }
           umma_commit(ACC_FULL(set));
         }
@@ -297,16 +293,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
     // released it: up to nKB x 16 KB of input in flight per SM, no registers involved
     if (elect_one()) {
       const uint32_t a0 = smem_u32(a_base);
-      int it = 0;
-      for (int w = blockIdx.x; w < a.n_items; w += gridDim.x, ++it) {
+      int g = 0;
+      for (int w = blockIdx.x; w < a.n_items; w += gridDim.x) {
         const int row0 = (w / a.n_groups) * K1_MT;
-        for (int kb = 0; kb < a.nKB; ++kb) {
-          mbar_wait(A_EMPTY(kb), (it & 1) ^ 1);
-          if (DBG && (a.dbgf & 2)) { mbar_arrive(RAW_FULL(kb)); continue; }
-          mbar_arrive_expect_tx(RAW_FULL(kb), K1_A_STAGE);
+        for (int kb = 0; kb < a.nKB; ++kb, ++g) {
+          const int st = g % NA;
+          mbar_wait(A_EMPTY(st), ((g / NA) & 1) ^ 1);
+          if (DBG && (a.dbgf & 2)) { mbar_arrive(RAW_FULL(st)); continue; }
+          mbar_arrive_expect_tx(RAW_FULL(st), K1_A_STAGE);
           const int c0 = kb * K1_KB;
-          if (c0 < a.C0) tma_load_box(a0 + (uint32_t)kb * K1_A_STAGE, &map0, c0, row0, RAW_FULL(kb));
-          else tma_load_box(a0 + (uint32_t)kb * K1_A_STAGE, &map1, c0 - a.C0, row0, RAW_FULL(kb));
+          if (c0 < a.C0) tma_load_box(a0 + (uint32_t)st * K1_A_STAGE, &map0, c0, row0, RAW_FULL(st));
+          else tma_load_box(a0 + (uint32_t)st * K1_A_STAGE, &map1, c0 - a.C0, row0, RAW_FULL(st));
         }
       }
     }
@@ -434,19 +431,25 @@ bool try_launch_conv1x1(const McvdOp& op, cudaStream_t s, int& rc) {
   const int Cin = op.C0 + op.C1, nKB = Cin / K1_KB;
   const int NT = op.i1;
   if (nKB < 1 || nKB > K1_MAX_KB || NT < 16 || NT > 256 || NT % 16 || op.Cout % NT) return false;
-  const size_t b_stage = (size_t)128 * NT;
   if (op.aux1 && op.H * op.W < 64) return false;        // norm-table staging covers <= 3 images per tile
+  const size_t b_stage = (size_t)128 * NT;
   const size_t tab_bytes = op.aux1 ? (size_t)2 * K1_TAB_IMGS * 3 * Cin * 4 : 0;
-  const size_t fixed = (size_t)nKB * K1_A_STAGE + (size_t)op.Cout * 4 + tab_bytes + 1024 + 1024;   // + barriers, + base alignment
   const size_t limit = 227 * 1024;
-  if (fixed + 2 * b_stage > limit) return false;
+  // the whole tile resident (every n-tile reuses the converted input) when it fits next to >= 2 weight stages,
+  // else a ring of >= 4 operand stages and one n-tile per work item
+  const size_t other = (size_t)op.Cout * 4 + tab_bytes + 1024 + 1024;     // bias, table, barriers, base alignment
+  int NA = nKB;
+  while (NA > 0 && (size_t)NA * K1_A_STAGE + other + 2 * b_stage > limit) --NA;
+  if (NA < nKB && NA > K1_RING) NA = K1_RING;
+  if (NA < 4 && NA < nKB) return false;
+  const size_t fixed = (size_t)NA * K1_A_STAGE + other;
   K1Args a;
   a.s0 = (const float*)op.src0; a.s1 = (const float*)op.src1; a.C0 = op.C0; a.C1 = op.C1;
   a.wpk = (const __half*)op.w; a.bias = (const float*)op.bias; a.res = (const float*)op.aux0;
   a.tab = (const float4*)op.aux1; a.dst = (float*)op.dst;
   a.Pimg = op.H * op.W; a.B = op.B; a.Cout = op.Cout;
   a.Qtot = (long long)op.B * a.Pimg;
-  a.NT = NT; a.tiles_n = op.Cout / NT; a.nKB = nKB;
+  a.NT = NT; a.tiles_n = op.Cout / NT; a.nKB = nKB; a.NA = NA;
   int NB = (int)((limit - fixed) / b_stage);
   a.NB = NB > 8 ? 8 : NB;
   a.nsets = (2 * NT <= 512) ? 2 : 1;
@@ -461,7 +464,7 @@ bool try_launch_conv1x1(const McvdOp& op, cudaStream_t s, int& rc) {
   // few m-tiles: spread the n-tiles of one m-tile over several CTAs (each converts its own copy of the input tile)
   int groups = 1;
   if (m_tiles < sms) groups = (int)(sms / m_tiles);
-  if (groups > a.tiles_n) groups = a.tiles_n;
+  if (groups > a.tiles_n || NA < nKB) groups = a.tiles_n;      // ring: one n-tile per item
   a.npg = (a.tiles_n + groups - 1) / groups;
   a.n_groups = (a.tiles_n + a.npg - 1) / a.npg;
   a.n_items = (int)m_tiles * a.n_groups;

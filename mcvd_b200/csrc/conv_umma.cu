@@ -422,6 +422,46 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       for (int acc = 0; acc < a.NACC; ++acc) {
         int myb = 0;
         const int mypix = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, myb);
+        if (!a.stats) {
+          // Row-per-lane drain (round 2, as in conv1x1_umma.cu): the lane writes the columns of its own position as
+          // 256-bit stores -- whole 32-byte sectors, no shared-memory transpose, a third of the instructions; the
+          // residual of a block is requested before the TMEM load is waited for.
+          const bool ok = mypix >= 0;
+          float* orow = dstp + (long long)mypix * a.Cout + n0;
+          const float* rrow = (resp && ok) ? resp + (long long)mypix * a.Cout + n0 : nullptr;
+          for (int blk = 0; blk < nblk; ++blk) {
+            const int cb = blk * 32;
+            const int w = min(32, a.NT - cb);               // 32 or 16 columns
+            float rr[32];
+            if (rrow) {
+#pragma unroll
+              for (int c8 = 0; c8 < 4; ++c8)
+                if (c8 * 8 < w) ldg256(rrow + cb + c8 * 8, rr + c8 * 8);
+            }
+            uint32_t r[32];
+            tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb), r);
+            if (w == 32) tmem_ld16(trow0 + (uint32_t)(acc * a.NT + cb + 16), r + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+              if (c8 * 8 < w) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cb + c8 * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias_s + cb + c8 * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  v[e] = __uint_as_float(r[c8 * 8 + e]) * a.wscale + bb[e];    // wscale is a power of two: exact product
+                  if (rrow) v[e] += rr[c8 * 8 + e];
+                  v[e] *= a.oscale;
+                  if (a.act_out) v[e] = silu_f(v[e]);
+                }
+                if (ok) stg256(orow + cb + c8 * 8, v);
+              }
+            }
+          }
+          continue;
+        }
         // statistics: image slot of this row inside its 128-position tile, and the slots present in this warp
         const long long q_tile = p0 + (long long)acc * MT;
         const int tile_b0 = (int)min((long long)(a.B - 1), q_tile / a.Pimg);

@@ -16,6 +16,12 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     if torch.cuda.is_available():
+        # a deadlocked kernel must cost minutes, not the whole GPU session: pytest-timeout's thread method dumps the
+        # stacks and exits the process even while the main thread sits in cudaStreamSynchronize
+        if config.pluginmanager.hasplugin("timeout"):
+            for it in items:
+                if "gpu" in it.keywords and it.get_closest_marker("timeout") is None:
+                    it.add_marker(pytest.mark.timeout(240, method="thread"))
         return
     skip = pytest.mark.skip(reason="no CUDA device")
     for it in items:

@@ -405,7 +405,12 @@ K1_CASES = [
     (40, 16, 192, 0, 576, True, False, False, False),      # 80 m tiles x 3 n tiles per CTA
     (8, 64, 96, 96, 96, False, False, False, False),       # 256 m tiles: several work items per CTA (phase wrap)
     (6, 64, 96, 0, 288, True, False, True, False),
-    (2, 8, 384, 0, 96, False, False, False, False),        # 12 K-blocks: not resident -> general kernel
+    (2, 8, 384, 0, 96, False, False, False, False),        # 12 K-blocks, still resident next to small weight stages
+    (4, 8, 384, 0, 1152, True, False, False, False),       # 8x8 q/k/v: ring of operand stages, one n tile per item
+    (3, 8, 384, 384, 192, False, False, True, False),      # 24 K-blocks from two sources through the ring, residual
+    (2, 16, 512, 0, 256, True, True, False, True),
+    (10, 64, 32, 0, 64, True, False, False, False),        # one K-block (a single operand stage), 320 m tiles
+    (3, 16, 32, 32, 32, False, False, True, False),
 ]
 
 
