@@ -108,7 +108,8 @@ class ClockSampler:
                               ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -386,7 +387,10 @@ def main():
     log(f"resident: {ms / args.steps:.1f} ms/step -> {value:.1f} frames/s")
     for i in range(min(args.warmup, 1)):
         step_e2e(i)
+    clocks2 = ClockSampler(local)                                    # the e2e region is clock-sampled too
+    clocks2.start()
     ms_e2e = timed(step_e2e, args.steps)
+    clk_e2e = clocks2.stop()
     e2e_val = frames_per_step * args.steps / (ms_e2e / 1e3)
     log(f"e2e: {ms_e2e / args.steps:.1f} ms/step -> {e2e_val:.1f} frames/s")
 
@@ -410,7 +414,8 @@ def main():
         "e2e": {"value": e2e_val, "unit": "frames/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": (x_host.numel() + cond_host.numel()) * 4 * world,
                 "d2h_bytes_per_step": n_clips * C * nfp * S * S * 4,
-                "allgather_bytes_per_rank_per_step": (B * C * nfp * S * S * 4) if world > 1 else 0},
+                "allgather_bytes_per_rank_per_step": (B * C * nfp * S * S * 4) if world > 1 else 0,
+                "clocks": clk_e2e},
         "gpu_launches": int(launches_per_step * args.steps),
         "clocks": clk,
         "frames_generated_per_s": gen_frames * args.steps / (ms / 1e3),
