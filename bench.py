@@ -501,14 +501,14 @@ def roofline(net, P, B, cfg, pk, pk_src):
         if os.path.exists(tpath) and "cfg2" in getattr(cfg, "workload", "") and B == 64:
             tj = json.load(open(tpath))
             out["traffic"] = tj["dram_bytes_per_launch_mean"]
-            out["traffic_note"] = (f"mean dram__bytes_read+write per k_conv_umma launch from the committed ncu pass "
+            out["traffic_note"] = (f"mean dram__bytes_read+write per conv launch ({tj['kernel']}) from the committed ncu pass "
                                    f"({tj['launches_per_forward']} launches, {tj['dram_bytes_per_forward'] / 1e9:.2f} GB per "
                                    f"forward); algorithmic {alg_bytes / 1e9:.2f} GB per forward")
         out["algorithmic_bytes_per_launch"] = alg_bytes / max(n_umma, 1)
         ms_umma = tot[conv_kind][0] / reps
         ach = flops_umma / (ms_umma / 1e3) / 1e12
-        out.update(kernel=("k_conv_umma" if conv_kind == lib.OP_CONV_UMMA else "k_conv_umma2 (cta_group::2)") +
-                          " (tcgen05 implicit-GEMM conv, all conv launches of one forward)",
+        out.update(kernel=("k_conv_umma (3x3) + k_conv1x1_umma (1x1)" if conv_kind == lib.OP_CONV_UMMA
+                           else "k_conv_umma2 (cta_group::2)") + " (tcgen05 implicit-GEMM convs, all conv launches of one forward)",
                    achieved=ach, frac=ach / pk["bf16_tflops_sustained"], executed_tflops=3 * ach,
                    executed_frac=3 * ach / pk["bf16_tflops_sustained"],
                    kernel_share_of_forward=ms_umma / total_ms,
