@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k_conv1x1_umma(const __grid_con
           for (int c8 = 0; c8 < 4; ++c8)
             if (cb + c8 * 8 < a.NT) ldg256(rp + c8 * 8, rr + c8 * 8);
         };
+        if (resp && ok) {                                    // later blocks' residual: into L2 while the MMAs run
+          const float* rp = resp + p * a.Cout + n0;
+          for (int blk = hsel + 2; blk < nblk; blk += 2) prefetch_l2(rp + blk * 32);
+        }
         if (hsel < nblk) res_fetch(hsel);
         K1_ACC(d10, te);
         mbar_wait(ACC_FULL(set), (tc / a.nsets) & 1);

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
   uint8_t* a_base = smem_raw;
   uint8_t* b_base = a_base + 2 * a_stage_bytes;
   float4* pads = reinterpret_cast<float4*>(b_base + (size_t)a.NB * b_stage_bytes);   // 4 warps x [32][8] float4
-  uint64_t* bars = reinterpret_cast<uint64_t*>(pads + 4 * 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(pads + (a.stats ? 4 * 256 : 0));   // transpose pads only with statistics
   // bars: a_full[2], a_empty[2], acc_full[2], acc_empty[2], b_full[NB], b_empty[NB]
   const uint32_t bar0 = smem_u32(bars);
   auto A_FULL = [&](int i) { return bar0 + 8u * i; };
@@ -414,6 +414,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_conv_umma(const UmmaArgs a) {
       asm volatile("bar.sync 2, 128;" ::: "memory");           // previous tile's readers are done
       for (int i = et; i < a.NT; i += 128) bias_s[i] = a.bias ? __ldg(a.bias + n0 + i) : 0.f;
       asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (resp && !a.stats) {
+        // the residual rows of this tile are pulled into L2 while its MMAs are still running (the epilogue warps
+        // would only be waiting): the drain below then pays an L2 hit per block instead of a DRAM round trip
+        for (int acc = 0; acc < a.NACC; ++acc) {
+          int bb = 0;
+          const int px = decode_pos(a, p0 + (long long)acc * MT + lq * 32 + lane, bb);
+          if (px >= 0) {
+            const float* rp = resp + (long long)px * a.Cout + n0;
+            for (int c = 0; c < a.NT; c += 32) prefetch_l2(rp + c);
+          }
+        }
+      }
       DBG_T(te);
       mbar_wait(ACC_FULL(set), (it / a.nsets) & 1);
       DBG_ADD(9, te, tid == W_EPI * 32);
@@ -710,7 +722,7 @@ int launch_conv_umma(const McvdOp& op, cudaStream_t s) {
   const size_t a_stage = (size_t)2 * (a.KB / 8) * a.HP * 16;
   const size_t b_stage = (size_t)(a.KB / 16) * 64 * a.NT;
   const size_t stat_bytes = a.stats ? (size_t)a.NJ * 2 * a.NT * 8 : 0;
-  const size_t fixed = 2 * a_stage + 4 * 4096 + 256 + (size_t)2 * TAB_NB * 32 * 16 + 1024 + stat_bytes;   // ... + bias + stats
+  const size_t fixed = 2 * a_stage + (a.stats ? 4 * 4096 : 0) + 256 + (size_t)2 * TAB_NB * 32 * 16 + 1024 + stat_bytes;   // ... + bias + stats
   const size_t limit = 227 * 1024;
   MCVD_CHECK(fixed + 2 * b_stage <= limit, "CONV_UMMA: tile does not fit shared memory (W=%d)", op.W);
   int NB = (int)((limit - fixed) / b_stage);
