@@ -160,8 +160,73 @@ __global__ void __launch_bounds__(128) k_linear(const float* __restrict__ src, c
   }
 }
 
+// Batched rows (per-clip timesteps: module.forward(x, labels) as the reference's own samplers call it).  The old path
+// above evaluated act_in(src[b, k]) once per OUTPUT (33k x 64 x 384 SiLUs for the FiLM projection: 0.86 ms); here a
+// block stages act_in of 16 batch rows in shared memory once and its 8 warps walk 64 output columns against them.
+// Per-row arithmetic (k = lane*4 + 128*it, x,y,z,w in order, xor-shuffle tree) is exactly the single-row path's, so a
+// batch of equal timesteps reproduces the uniform-timestep evaluation bit for bit.
+constexpr int LIN_COLS = 64;
+
+__global__ void __launch_bounds__(256) k_linear_batched(const float* __restrict__ src, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, float* __restrict__ dst, int B,
+                                                        int K, int N, int flags) {
+  extern __shared__ __align__(16) float lin_xs[];            // [LIN_BT][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * LIN_COLS;
+  for (int b0 = 0; b0 < B; b0 += LIN_BT) {
+    __syncthreads();                                         // previous tile's readers are done
+    for (int i = threadIdx.x; i < LIN_BT * K; i += blockDim.x) {
+      const int r = i / K, k = i - r * K;
+      float xv = 0.f;
+      if (b0 + r < B) {
+        xv = src[(long long)(b0 + r) * K + k];
+        if (flags & MCVD_F_ACT_IN) xv = silu_f(xv);
+      }
+      lin_xs[i] = xv;
+    }
+    __syncthreads();
+    for (int c = warp; c < LIN_COLS; c += 8) {
+      const int j = j0 + c;
+      if (j >= N) break;
+      const float* wr = w + (long long)j * K;
+      float acc[LIN_BT];
+#pragma unroll
+      for (int i = 0; i < LIN_BT; ++i) acc[i] = 0.f;
+      for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+        for (int i = 0; i < LIN_BT; ++i) {
+          const float4 xv = *reinterpret_cast<const float4*>(lin_xs + i * K + k);
+          acc[i] = fmaf(wv.x, xv.x, acc[i]); acc[i] = fmaf(wv.y, xv.y, acc[i]);
+          acc[i] = fmaf(wv.z, xv.z, acc[i]); acc[i] = fmaf(wv.w, xv.w, acc[i]);
+        }
+      }
+      const float bj = bias ? bias[j] : 0.f;
+#pragma unroll
+      for (int i = 0; i < LIN_BT; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && b0 + i < B) {
+          v += bj;
+          if (flags & MCVD_F_ACT_OUT) v = silu_f(v);
+          dst[(long long)(b0 + i) * N + j] = v;
+        }
+      }
+    }
+  }
+}
+
 int launch_linear(const McvdOp& op, cudaStream_t s) {
   MCVD_CHECK(op.src0 && op.w && op.dst, "LINEAR: null pointer");
+  const size_t xs_bytes = (size_t)LIN_BT * op.C0 * sizeof(float);
+  if (op.B > 1 && (op.C0 & 3) == 0 && xs_bytes <= 48 * 1024 && (((uintptr_t)op.w | (uintptr_t)op.src0) & 15) == 0) {
+    k_linear_batched<<<cdiv(op.Cout, LIN_COLS), 256, xs_bytes, s>>>((const float*)op.src0, (const float*)op.w,
+                                                                     (const float*)op.bias, (float*)op.dst, op.B, op.C0,
+                                                                     op.Cout, op.flags);
+    MCVD_CUDA_LAUNCH_CHECK("linear");
+    return 0;
+  }
   k_linear<<<cdiv(op.Cout, 4), 128, 0, s>>>((const float*)op.src0, (const float*)op.w, (const float*)op.bias,
                                             (float*)op.dst, op.B, op.C0, op.Cout, op.flags);
   MCVD_CUDA_LAUNCH_CHECK("linear");

@@ -262,6 +262,18 @@ def test_linear_embed_layout_update():
         run([mk(lib.OP_LINEAR, 1, C0=K, Cout=77, src0=xs.to(DEV), w=ws.to(DEV).contiguous(), bias=bs.to(DEV), dst=ys,
                 flags=lib.F_ACT_IN)])
         assert (ys.cpu() - ys_ref).abs().max().item() < 1e-5
+    # batched rows (per-clip timesteps): staged-activation kernel; a row equals the single-row evaluation bit for bit
+    Bb, K, N = 37, 384, 203
+    xb, wb, bb = rnd(Bb, K, seed=8), rnd(N, K, seed=9) * 0.1, rnd(N, seed=10)
+    yb_ref = F.silu(F.linear(F.silu(xb), wb, bb))
+    xbd, wbd, bbd = xb.to(DEV), wb.to(DEV).contiguous(), bb.to(DEV)
+    yb = torch.zeros(Bb, N, device=DEV)
+    run([mk(lib.OP_LINEAR, Bb, C0=K, Cout=N, src0=xbd, w=wbd, bias=bbd, dst=yb, flags=lib.F_ACT_IN | lib.F_ACT_OUT)])
+    assert (yb.cpu() - yb_ref).abs().max().item() < 1e-5
+    y1 = torch.zeros(1, N, device=DEV)
+    run([mk(lib.OP_LINEAR, 1, C0=K, Cout=N, src0=xbd[20:21].contiguous(), w=wbd, bias=bbd, dst=y1,
+            flags=lib.F_ACT_IN | lib.F_ACT_OUT)])
+    assert torch.equal(y1[0], yb[20])
     # layout round trip + diffusion update
     B, C, S = 2, 5, 16
     x, c = rnd(B, C, S, S, seed=3), rnd(B, 3, S, S, seed=4)
