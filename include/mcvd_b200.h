@@ -104,7 +104,11 @@ enum {
    * dst = f0 * (Conv_1(act(norm(h))) + Conv_2(x) + bias + residual) in ONE kernel.
    * dst2 = NULL, or the int64 tile statistics of the stored output (format and meaning as in MCVD_OP_CONV_UMMA2:
    * [tiles][NJ][2][Cout], mcvd_umma2_stats_bytes() bytes) for the GroupNorm that reads dst next;
-   * aux2 = NULL or int64 [grid][16] cycle counters (tools/umma_timing.py). */
+   * aux2 = NULL or int64 [grid][16] cycle counters (tools/umma_timing.py).
+   * Kernel size 1 without a second segment and without dst2 (NIN / q,k,v / skip projections,
+   * layers.py:541-556, layerspp.py:230-249,618-619) is served by the input-stationary kernel of
+   * mcvd_b200/csrc/conv1x1_umma.cu (same weights, bit-identical results) when the channel counts are multiples
+   * of 32 and, with a norm table, the maps hold >= 64 positions; MCVD_CONV1X1=0 in the environment disables it. */
   MCVD_OP_CONV_UMMA = 12,
   /* final 3x3 conv with tiny Cout (<= 16) and fused input norm: conv3x3(SiLU(GN(x))) of
    * ncsnpp_more.py:375-379; aux0 = float4 norm table or NULL. */
