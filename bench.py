@@ -67,7 +67,7 @@ def parse():
     ap.add_argument("--conv", default=None, choices=[None, "umma", "umma2", "simt"])
     ap.add_argument("--ar", action="store_true", help="time the full autoregressive video_gen loop (num_frames_pred frames)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
-    ap.add_argument("--cpu-batch", type=int, default=2)
+    ap.add_argument("--cpu-batch", type=int, default=0, help="clips per CPU-arm step (0 = 2, or 1 when --steps > 5)")
     ap.add_argument("--psnr-steps", type=int, default=0, help="DDPM steps of the PSNR check (default: the workload's)")
     return ap.parse_args()
 
@@ -207,13 +207,17 @@ class CpuArm:
             return n, {}
         ncpu = os.cpu_count() or 1
         scan = {}
-        self_threads = sorted({min(ncpu, 16), min(ncpu, 32), min(ncpu, 64), ncpu})
+        self_threads = sorted({min(ncpu, 8), min(ncpu, 16), min(ncpu, 32), min(ncpu, 64), ncpu})
         for n in self_threads:
             torch.set_num_threads(n)
             self.forward()
             t0 = time.perf_counter()
             self.forward()
             scan[n] = time.perf_counter() - t0
+            # ascending scan, stop at the first clear regression: on the 128-core GPU hosts one forward takes 0.08 s
+            # at 16 threads and 48 s at 128 -- trying every count would cost minutes of the arm's budget
+            if len(scan) >= 2 and scan[n] > 1.3 * min(scan.values()):
+                break
         best = min(scan, key=scan.get)
         torch.set_num_threads(best)
         return best, {str(k): round(v, 3) for k, v in scan.items()}
@@ -253,8 +257,12 @@ def run_reference_arm(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # clips per step: 2 for short runs, 1 when the driver asks for many steps (a step is a FULL sampler call, ~8 s per
+    # clip on the GPU hosts: K = 20 then stays within a few minutes); frames/s is per-clip work either way
+    if not args.cpu_batch:
+        args.cpu_batch = 2 if args.steps <= 5 else 1
     arm = CpuArm(cfg, args.workload, args.cpu_batch)
-    log(f"CPU arm: {arm.kind}, {arm.threads} threads, scan {arm.thread_scan}")
+    log(f"CPU arm: {arm.kind}, {arm.threads} threads, scan {arm.thread_scan}, {args.cpu_batch} clip(s) per step")
     for i in range(args.warmup):
         arm.forward()                                            # warm-up steps are single forwards (allocator, oneDNN)
     dts = [arm.sample() for _ in range(args.steps)]
