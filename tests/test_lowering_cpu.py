@@ -117,6 +117,35 @@ def test_video_gen_loop_lowering():
     assert O.psnr01(vid, ref) > 50.0
 
 
+def test_evaluate_clips_preds_per_test_plumbing(monkeypatch):
+    """The test-batch driver of the reference's video_gen (runners/ncsn_runner.py:1392-1395, 1463-1470, 1580-1609):
+    repeat_interleave by preds_per_test, conditioning split, AR generation, per-frame metrics, best repeat per clip.  The
+    GPU metric kernel is replaced by its oracle here (it has its own GPU parity test); everything else is the product
+    code on the CPU interpreter."""
+    from oracle import metrics_oracle as M
+    cfg, net, sd = cpu_module("tiny", "umma")
+    C, S = cfg.data.channels, cfg.data.image_size
+    nfp, p, nclips = 2, 3, 2
+    T = cfg.data.num_frames_cond + nfp
+    X = detfill.uniform("clips", (nclips, T, C, S, S), 0.0, 1.0)
+
+    def cpu_metrics(config, pred, real):
+        return torch.from_numpy(M.frame_metrics(pred.numpy(), real.numpy(), C))
+
+    monkeypatch.setattr(runner, "frame_metrics", cpu_metrics)
+    frames, m = runner.evaluate_clips(cfg, net, X, preds_per_test=p, num_frames_pred=nfp,
+                                      sampler=samplers.ddpm_sampler, sampler_kwargs=dict(subsample_steps=3),
+                                      philox_seed=None)
+    assert frames.shape == (nclips * p, C * nfp, S, S) and float(frames.min()) >= 0.0 and float(frames.max()) <= 1.0
+    assert m["per_frame"].shape == (nclips * p, nfp, 2)
+    assert m["mse"].shape == m["psnr"].shape == m["ssim"].shape == (nclips,)
+    # best-of-repeats: the product function against the oracle restatement on the same per-frame numbers
+    mse, psnr, ssim = M.best_of_repeats(m["per_frame"].numpy(), p)
+    assert np.allclose(m["mse"].numpy(), mse) and np.allclose(m["psnr"].numpy(), psnr) and np.allclose(m["ssim"].numpy(), ssim)
+    # repeats of one clip share the conditioning frames but are sampled with their own noise: they differ
+    assert not torch.equal(frames[0], frames[1])
+
+
 def test_warm_start_t_min_matches_reference_golden_and_oracle():
     """init_prev_t warm start (t_min > 0), replicated as the reference writes it (models/__init__.py:269-280)."""
     name = "tiny"
