@@ -4,23 +4,27 @@
 // (layerspp.py:230-249) and the 1x1 Conv_2 skip projection of ResnetBlockBigGANppGN (layerspp.py:595-624),
 // with the GroupNorm of the attention block folded into the staging exactly as conv_umma.cu does.
 //
-// Why a second kernel (profiles/r2_launch_metrics_v11_cfg2_b64.txt, profiles/r2_k1_attribution.txt): the general
+// Why a second kernel (profiles/r2_launch_metrics_v11_cfg2_b64.txt, profiles/r2_k1_attribution_{1,2,3}_*.txt): the general
 // kernel re-stages the transformed input once per n-tile and keeps one K-block of register-staged global loads in
 // flight, so a 192->576 projection ran at 8-10 % of the tensor pipe and ~1 TB/s of DRAM traffic.  A 1x1 convolution
 // has no halo and no taps, so here
-//   * a CTA owns a 128-position x Cin tile whose Cin/32 K-blocks are ALL resident in shared memory (Cin <= 320) and
-//     loops over every n-tile of the output against that resident tile: the input is converted once;
+//   * a CTA owns a 128-position x Cin tile whose Cin/32 K-blocks are ALL resident in shared memory (when they fit next
+//     to two weight stages: Cin <= 320 for the shapes of this network) and loops over every n-tile of the output
+//     against that resident tile: the input is converted once.  Wider inputs stream through a ring of 8 operand
+//     stages with one n-tile per work item (the 384-channel 8x8 level);
 //   * the raw fp32 [128 x 32] box of a K-block is brought in by TMA (128-byte swizzle) straight into that K-block's
 //     operand stage the moment the previous tile's MMAs released it -- up to Cin/32 x 16 KB in flight per SM with no
 //     registers involved (register-staged loads capped the first version at ~2 TB/s) -- and is converted IN PLACE:
 //     the 128 threads of a producer group read their rows, meet at a named barrier, and write the fp16 hi | lo
 //     core-matrix image over it (16 KB either way);
-//   * the two producer groups take alternating K-blocks.
+//   * the two producer groups own alternating operand STAGES (even / odd): a stage's barriers are then only ever
+//     waited on by one group, in order -- a group that could run a whole phase ahead of another group's stage would
+//     alias the mbarrier parity bit (a real deadlock on 32-channel inputs before this rule).
 // The weight images, operand split and epilogue arithmetic are those of conv_umma.cu (same packed-weight format), so
 // results are bit-identical to the general kernel's (tests/test_gpu_ops.py::test_conv1x1_stationary).
 //
 // Warp roles (608 threads, one CTA per SM):
-//   warps 0-3 / 4-7  producer groups 0 / 1: K-blocks kb = group, group + 2, ...
+//   warps 0-3 / 4-7  producer groups 0 / 1: operand stages st = group, group + 2, ...
 //   warp  8          weight loader: cp.async.bulk of the packed fp16 hi/lo stage images (ring of NB stages)
 //   warp  9          TMEM allocation + single-thread tcgen05.mma issue
 //   warps 10-17      epilogue: two warps per TMEM lane quadrant, alternating 32-column blocks; every lane owns one
