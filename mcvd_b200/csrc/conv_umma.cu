@@ -21,16 +21,24 @@
 //     [k-chunk of 8 halfs][position][8 halfs = 16 B]      LBO = positions*16 B,  SBO = 128 B.
 // Outputs at padding positions are computed and discarded (2..20 % of the rows).
 //
-// Round 2 (measurements in profiles/r2_*): a second MMA-issuing warp (one per accumulator: a single thread's
-// instruction stream, ~8 instructions per MMA at ~7 cycles each, was as slow as the tensor core itself), and the
-// GroupNorm partial sums of the stored output accumulated in the epilogue in exact 64-bit fixed point (replaces
-// the k_gn_partial pass; same format and rationale as conv_umma2.cu).
+// Round 2 (measurements in profiles/r2_*):
+//   * a second MMA-issuing warp (one per accumulator: a single thread's instruction stream, ~8 instructions per MMA at
+//     ~7 cycles each, was as slow as the tensor core itself);
+//   * row-per-lane epilogue: a lane owns one output position and writes its columns with 256-bit stores, the residual
+//     rows of the tile are prefetched into L2 while the accumulators are still pending; the shared-memory transpose
+//     remains only for the optional tile statistics;
+//   * optional GroupNorm partial sums of the stored output in exact 64-bit fixed point from the epilogue (op.dst2;
+//     same format and rationale as conv_umma2.cu; off by default);
+//   * two producer threads per row on 128-row slabs, centre-rows-only staging of the fused-shortcut K-blocks;
+//   * plain 1x1 convolutions are handed to the input-stationary kernel of conv1x1_umma.cu by launch_conv_umma.
 //
-// Warp roles (one CTA per SM):
-//   warps 0-7  producers: fp32 NHWC global -> normalise/FiLM/SiLU -> fp16 hi/lo -> smem slab
-//              (generic-proxy stores + fence.proxy.async), then the epilogue (TMEM -> regs -> global)
-//   warp  8    weight loader: cp.async.bulk (TMA 1-D) of pre-packed fp16 hi/lo smem images
-//   warp  9    TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+// Warp roles (480 threads, one CTA per SM):
+//   warps 0-7   producers: fp32 NHWC global -> normalise/FiLM/SiLU -> fp16 hi/lo -> smem slab
+//               (generic-proxy stores + fence.proxy.async)
+//   warp  8     weight loader: cp.async.bulk (TMA 1-D) of pre-packed fp16 hi/lo smem images
+//   warp  9     TMEM allocation + tcgen05.mma issue for accumulator 0, tcgen05.commit -> mbarriers
+//   warps 10-13 epilogue (TMEM lane quadrants 2,3,0,1): TMEM -> registers -> bias / residual / scale -> global
+//   warp  14    tcgen05.mma issue for accumulator 1 of two-accumulator tiles
 #include <cuda_fp16.h>
 
 #include "mcvd_common.cuh"
