@@ -109,8 +109,8 @@ __device__ __forceinline__ int decode_pos(const UmmaArgs& a, long long q, int& b
 // ---- the kernel: persistent CTAs, all phases overlapped ----------------------------------------------
 //   warps 0-7   producers : fp32 NHWC global -> normalise/FiLM/SiLU -> fp16 hi/lo -> smem slab (2 stages)
 //   warp  8     loader    : cp.async.bulk of the pre-packed fp16 hi/lo weight images (ring of NB stages)
-//   warp  9     MMA       : TMEM allocation, single-thread tcgen05.mma issue, commits -> mbarriers
-//   warps 10-13 epilogue  : TMEM -> registers -> swizzled smem transpose -> 128-byte-line global stores
+//   warps 9,14  MMA       : TMEM allocation (9), one tcgen05.mma-issuing thread per accumulator, commits -> mbarriers
+//   warps 10-13 epilogue  : TMEM -> registers -> row-per-lane 256-bit global stores (smem transpose with statistics)
 // A CTA walks tiles blockIdx.x, +gridDim.x, ...; the A/B pipelines run across tile boundaries and the
 // accumulator is double-buffered in TMEM (when 2 * NACC * NT <= 512), so the producers of tile i+1, the
 // MMAs of tile i+1 and the epilogue of tile i all run concurrently, and CTAs drift out of lock-step.
